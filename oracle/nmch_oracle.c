@@ -1,0 +1,695 @@
+/*
+ * nmch_oracle.c -- CPU oracle for the Heston Monte-Carlo hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see nmch_oracle.h).  Plain C99 + OpenMP; single
+ * precision where the reference is single precision, explicit fmaf() where
+ * nvcc contracts the reference's expressions (read off
+ * the SASS of FE_k2<XORWOW> at sm_100).
+ *
+ * Parity status: pinned -- see tests/test_oracle_*.py (Philox KATs, cuRAND
+ * host build, reference CUDA build fixtures).  Host libm (logf/sinf/cosf)
+ * differs from the device in the last bits (cuRAND's device Box-Muller uses
+ * __sincosf, curand_normal.h:76-83), so float outputs are compared with the
+ * tolerances written in the tests; integer streams are bit exact.
+ */
+#include "nmch_oracle.h"
+
+#include <complex.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ======================================================================== */
+/* Philox4x32-10  (curand_philox4x32_x.h:88-91, 160-192; Random123)          */
+/* ======================================================================== */
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int round = 0; round < 10; ++round) {
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* ======================================================================== */
+/* XORWOW  (curand_kernel.h:863-874 step, :800-825 init, :721-736 skip)      */
+/* ======================================================================== */
+static inline void xorwow_advance_v(uint32_t v[5])
+{
+    uint32_t t = v[0] ^ (v[0] >> 2);
+    v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+    v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+}
+
+/* 160x160 GF(2) matrices as 160 rows of 5 words; row b is the image of the
+ * unit vector e_b, so   v*M = XOR of the rows selected by the set bits of v
+ * (the convention of __curand_matvec_inplace, curand_kernel.h:315-334).
+ * cuRAND ships these as tables (curand_precalc.h); the oracle derives them:
+ * seq[m] advances by 2^67 * 4^m draws, off[m] by 4^m draws. */
+typedef struct { uint32_t row[160][5]; } gf2mat_t;
+
+static void gf2_matvec(const uint32_t v[5], const gf2mat_t *M, uint32_t out[5])
+{
+    uint32_t r[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 32; ++j)
+            if (v[i] & (1u << j))
+                for (int k = 0; k < 5; ++k) r[k] ^= M->row[i * 32 + j][k];
+    memcpy(out, r, sizeof r);
+}
+
+static void gf2_square(const gf2mat_t *M, gf2mat_t *out)
+{
+    gf2mat_t tmp;
+    for (int b = 0; b < 160; ++b) gf2_matvec(M->row[b], M, tmp.row[b]);
+    *out = tmp;
+}
+
+static gf2mat_t g_seq[32], g_off[32];
+static int g_mats_ready = 0;
+
+static void xorwow_build_matrices(void)
+{
+    if (g_mats_ready) return;
+#ifdef _OPENMP
+#pragma omp critical(orc_mats)
+#endif
+    {
+        if (!g_mats_ready) {
+            gf2mat_t cur;
+            for (int b = 0; b < 160; ++b) {
+                uint32_t e[5] = {0, 0, 0, 0, 0};
+                e[b / 32] = 1u << (b % 32);
+                xorwow_advance_v(e);
+                memcpy(cur.row[b], e, sizeof e);
+            }
+            /* off[m] = T^(4^m), m = 0..31 ; after 64 squarings cur = T^(2^64) */
+            for (int m = 0; m < 32; ++m) {
+                g_off[m] = cur;
+                gf2_square(&cur, &cur);
+                gf2_square(&cur, &cur);
+            }
+            /* three more squarings: T^(2^67) */
+            gf2_square(&cur, &cur);
+            gf2_square(&cur, &cur);
+            gf2_square(&cur, &cur);
+            for (int m = 0; m < 32; ++m) {
+                g_seq[m] = cur;
+                gf2_square(&cur, &cur);
+                gf2_square(&cur, &cur);
+            }
+            g_mats_ready = 1;
+        }
+    }
+}
+
+static void xorwow_init(orc_rng_t *s, uint64_t seed, uint64_t subsequence, uint64_t offset)
+{
+    xorwow_build_matrices();
+    /* seed scramble, curand_kernel.h:807-818 */
+    uint32_t s0 = (uint32_t)seed ^ 0xaad26b49u;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0;
+    uint32_t t1 = 2591861531u * s1;
+    s->d = 6615241u + t1 + t0;
+    s->v[0] = 123456789u + t0;
+    s->v[1] = 362436069u ^ t0;
+    s->v[2] = 521288629u + t1;
+    s->v[3] = 88675123u ^ t1;
+    s->v[4] = 5783321u + t0;
+    /* subsequence skip: 2-bit digits, LSB first (curand_kernel.h:721-736) */
+    uint64_t x = subsequence;
+    for (int m = 0; x; ++m, x >>= 2)
+        for (unsigned t = 0; t < (x & 3u); ++t) gf2_matvec(s->v, &g_seq[m], s->v);
+    /* offset skip (curand_kernel.h:703-719) */
+    x = offset;
+    for (int m = 0; x; ++m, x >>= 2)
+        for (unsigned t = 0; t < (x & 3u); ++t) gf2_matvec(s->v, &g_off[m], s->v);
+    s->d += 362437u * (uint32_t)offset;
+}
+
+static inline uint32_t xorwow_next(orc_rng_t *s)
+{
+    xorwow_advance_v(s->v);
+    s->d += 362437u;
+    return s->v[4] + s->d;
+}
+
+/* ======================================================================== */
+/* generic stream front-end                                                  */
+/* ======================================================================== */
+static void philox_incr(uint32_t c[4], uint64_t n)
+{   /* Philox_State_Incr(s, n), curand_philox4x32_x.h:107-122 */
+    uint32_t nlo = (uint32_t)n, nhi = (uint32_t)(n >> 32);
+    c[0] += nlo;
+    if (c[0] < nlo) nhi++;
+    c[1] += nhi;
+    if (nhi <= c[1]) return;
+    if (++c[2]) return;
+    ++c[3];
+}
+
+void orc_rng_init(orc_rng_t *s, int kind, uint64_t seed, uint64_t subsequence, uint64_t offset)
+{
+    memset(s, 0, sizeof *s);
+    s->kind = kind;
+    if (kind == ORC_RNG_XORWOW) {
+        xorwow_init(s, seed, subsequence, offset);
+    } else {
+        /* curand_init for Philox, curand_kernel.h:1022-1037, skipahead :971-981 */
+        s->key[0] = (uint32_t)seed;
+        s->key[1] = (uint32_t)(seed >> 32);
+        s->ctr[2] = (uint32_t)subsequence;
+        s->ctr[3] = (uint32_t)(subsequence >> 32);
+        s->pos = (int)(offset & 3u);
+        philox_incr(s->ctr, offset / 4);
+        orc_philox4x32_10(s->ctr, s->key, s->out);
+    }
+}
+
+uint32_t orc_rng_next(orc_rng_t *s)
+{
+    if (s->kind == ORC_RNG_XORWOW) return xorwow_next(s);
+    /* curand(), curand_kernel.h:888-912 */
+    uint32_t r = s->out[s->pos++];
+    if (s->pos == 4) {
+        philox_incr(s->ctr, 1);
+        orc_philox4x32_10(s->ctr, s->key, s->out);
+        s->pos = 0;
+    }
+    return r;
+}
+
+/* ======================================================================== */
+/* float transforms                                                          */
+/* ======================================================================== */
+#define TWO_POW32_INV      2.3283064e-10f
+#define TWO_POW32_INV_2PI  (2.3283064e-10f * 6.2831855f)
+#define TWO_POW53_INV_D    1.1102230246251565e-16
+
+static inline float uniform_from_u32(uint32_t x)
+{   /* _curand_uniform, curand_uniform.h:69-72 ; nvcc contracts to one FFMA */
+    return fmaf((float)x, TWO_POW32_INV, TWO_POW32_INV / 2.0f);
+}
+
+float orc_uniform(orc_rng_t *s) { return uniform_from_u32(orc_rng_next(s)); }
+
+static inline void box_muller(uint32_t x, uint32_t y, float *gx, float *gy)
+{   /* _curand_box_muller, curand_normal.h:70-87 : .x pairs with sin */
+    float u = fmaf((float)x, TWO_POW32_INV, TWO_POW32_INV / 2);
+    float v = fmaf((float)y, TWO_POW32_INV_2PI, TWO_POW32_INV_2PI / 2);
+    float s = sqrtf(-2.0f * logf(u));
+    *gx = sinf(v) * s;
+    *gy = cosf(v) * s;
+}
+
+void orc_normal2(orc_rng_t *s, float *gx, float *gy)
+{   /* curand_normal2, curand_normal.h:405-408, 424-427 */
+    uint32_t x = orc_rng_next(s);
+    uint32_t y = orc_rng_next(s);
+    box_muller(x, y, gx, gy);
+}
+
+float orc_normal(orc_rng_t *s)
+{   /* curand_normal (cached pair), curand_normal.h:313-326 / 345-358 */
+    if (s->bm_flag != 1) {
+        float gx, gy;
+        orc_normal2(s, &gx, &gy);
+        s->bm_extra = gy;
+        s->bm_flag = 1;
+        return gx;
+    }
+    s->bm_flag = 0;
+    return s->bm_extra;
+}
+
+double orc_normal_double(orc_rng_t *s)
+{   /* curand_normal_double, curand_normal.h:581-596 / 615-627 ;
+       _curand_box_muller_double :110-133 (host branch: sin/cos(v*pi)) */
+    if (s->bm_flag_d != 1) {
+        uint32_t x0 = orc_rng_next(s), x1 = orc_rng_next(s);
+        uint32_t y0 = orc_rng_next(s), y1 = orc_rng_next(s);
+        uint64_t zx = (uint64_t)x0 ^ ((uint64_t)x1 << (53 - 32));
+        double u = zx * TWO_POW53_INV_D + (TWO_POW53_INV_D / 2.0);
+        uint64_t zy = (uint64_t)y0 ^ ((uint64_t)y1 << (53 - 32));
+        double v = zy * (TWO_POW53_INV_D * 2.0) + TWO_POW53_INV_D;
+        double r = sqrt(-2.0 * log(u));
+        double gx = sin(v * 3.1415926535897932) * r;
+        double gy = cos(v * 3.1415926535897932) * r;
+        s->bm_extra_d = gy;
+        s->bm_flag_d = 1;
+        return gx;
+    }
+    s->bm_flag_d = 0;
+    return s->bm_extra_d;
+}
+
+/* ---- curand_poisson, curand_poisson.h:594-601 ---------------------------- */
+/* host branches of __cr_* (curand_poisson.h:74-113) use exact libm; the
+ * device uses rsqrt/ex2/lg2/rcp.approx -- accept/reject may differ in rare
+ * edge cases, so EM parity host-vs-device is statistical (tests say so). */
+static inline float cr_rsqrt(float a) { return 1.0f / sqrtf(a); }
+static inline float cr_exp(float a) { return expf(a); }
+static inline float cr_log(float a) { return logf(a); }
+static inline float cr_rcp(float a) { return 1.0f / a; }
+
+static float cr_pgammainc(float a, float x)
+{   /* curand_poisson.h:116-147 */
+    const float ma1 = 1.43248035075540910f, ma2 = 0.12400979329415655f, ma3 = 0.00025361074907033f,
+                mb1 = 0.21096734870196546f, mb2 = 1.97381164089999420f, mb3 = 0.94201734077887530f;
+    float alpha = cr_rsqrt(a - ma2);
+    alpha = ma1 * alpha + ma3;
+    float beta = cr_rsqrt(a - mb2);
+    beta = mb1 * beta + mb3;
+    float t = a - x;
+    t = alpha * t - beta;
+    t = 1.0f + cr_exp(t);
+    t = t * t;
+    t = cr_rcp(t);
+    return t;
+}
+
+static float cr_pgammaincinv(float a, float y)
+{   /* curand_poisson.h:150-180 */
+    const float ma1 = 1.43248035075540910f, ma2 = 0.12400979329415655f, ma3 = 0.00025361074907033f,
+                mb1 = 0.21096734870196546f, mb2 = 1.97381164089999420f, mb3 = 0.94201734077887530f;
+    float alpha = cr_rsqrt(a - ma2);
+    alpha = ma1 * alpha + ma3;
+    float beta = cr_rsqrt(a - mb2);
+    beta = mb1 * beta + mb3;
+    float t = cr_rsqrt(y) - 1.0f;
+    t = cr_log(t);
+    t = beta + t;
+    t = -t * cr_rcp(alpha) + a;
+    return t;
+}
+
+/* device float->int conversion saturates (cvt.rzi.s32.f32: NaN -> 0, +-inf -> INT_MAX/INT_MIN);
+ * x86 would give INT_MIN.  Reached when curand_uniform returns exactly 1.0f (x = +inf, rejected). */
+static inline int sat_f2i(float f)
+{
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)f;
+}
+
+static double cr_lgamma_integer(int a)
+{   /* curand_poisson.h:199-243 (Stirling, Hart et al. 5404) */
+    static const double table[] = {0.0, 0.0, 6.931471805599453094e-1, 1.791759469228055001e0,
+        3.178053830347945620e0, 4.787491742782045994e0, 6.579251212010100995e0,
+        8.525161361065414300e0, 1.060460290274525023e1};
+    double s, t, sum;
+    double fa = fabs((float)a);
+    if (a > 8) {
+        s = 1.0 / fa;
+        t = s * s;
+        sum = -0.1633436431e-2;
+        sum = sum * t + 0.83645878922e-3;
+        sum = sum * t - 0.5951896861197e-3;
+        sum = sum * t + 0.793650576493454e-3;
+        sum = sum * t - 0.277777777735865004e-2;
+        sum = sum * t + 0.833333333333331018375e-1;
+        sum = sum * s + 0.918938533204672;
+        s = 0.5 * log(fa);
+        t = fa - 0.5;
+        s = s * t;
+        t = s - fa;
+        s = s + sum;
+        t = t + s;
+        return t;
+    }
+    int idx = (int)fa - 1;
+    if (idx < 0 || idx > 8) return 0.0;     /* device reads out of the table here; the draw is rejected anyway */
+    return table[idx];
+}
+
+static unsigned poisson_knuth(orc_rng_t *s, float lambda)
+{   /* curand_poisson.h:246-257 */
+    unsigned k = 0;
+    float p = expf(lambda);
+    do {
+        k++;
+        p *= orc_uniform(s);
+    } while (p > 1.0);
+    return k - 1;
+}
+
+static unsigned poisson_gammainc(orc_rng_t *s, float lambda)
+{   /* curand_poisson.h:464-481 */
+    float y, x, t, z, v;
+    float logl = cr_log(lambda);
+    for (;;) {
+        y = orc_uniform(s);
+        x = cr_pgammaincinv(lambda, y);
+        x = floorf(x);
+        z = orc_uniform(s);
+        v = (cr_pgammainc(lambda, x + 1.0f) - cr_pgammainc(lambda, x)) * 1.3f;
+        z = z * v;
+        t = (float)cr_exp(-lambda + x * logl - (float)cr_lgamma_integer(sat_f2i(1.0f + x)));
+        if ((z < t) && (v >= 1e-20)) break;
+    }
+    return (unsigned)x;
+}
+
+unsigned orc_poisson(orc_rng_t *s, double lambda)
+{
+    if (lambda < 64) return poisson_knuth(s, (float)lambda);
+    if (lambda > 4000) return (unsigned)((sqrt(lambda) * orc_normal_double(s)) + lambda + 0.5);
+    return poisson_gammainc(s, (float)lambda);
+}
+
+/* ---- gamma_distribution, src/NMCH/methods/NMCH_EM.cu:11-55 --------------- */
+float orc_gamma(orc_rng_t *s, float alpha)
+{
+    float d, c, x, v, u, x2;
+    float C = 1.0f;
+    if (alpha < 1.0f) {                       /* NMCH_EM.cu:35-38 */
+        C = powf(orc_uniform(s), 1.0f / alpha);
+        alpha += 1.0f;
+    }
+    d = alpha - 1.0f / 3.0f;                  /* :41 */
+    c = 1.0f / sqrtf(9.0f * d);               /* :42 */
+    for (;;) {                                /* :44-54 */
+        do { x = orc_normal(s); v = fmaf(c, x, 1.0f); } while (v <= 0.0f);
+        v = v * v * v;
+        u = orc_uniform(s);
+        x2 = x * x;
+        if (u < 1.0f - 0.0331f * x2 * x2 ||
+            logf(u) < 0.5f * x2 + d * (1.0f - v + logf(v))) return d * v * C;
+    }
+}
+
+/* ======================================================================== */
+/* FE  (NMCH_FE.cu:145-175; contraction as SURVEY.md Appendix B)             */
+/* ======================================================================== */
+static inline void fe_step(float *S, float *V, float gx, float gy, float r, float k, float rho,
+                           float theta, float sigma, float dt, float sqrt_dt, float sqrt_rho,
+                           int floor_kind)
+{
+    float St = *S, Vt = *V;
+    float sv = sqrtf(Vt);
+    float a = r * St;          a = fmaf(a, dt, St);
+    float z = gy * sqrt_rho;   z = fmaf(gx, rho, z);
+    float b = sv * St;         b = b * sqrt_dt;
+    float Sn = fmaf(b, z, a);
+    float c = theta - Vt;      c = c * k;   c = fmaf(c, dt, Vt);
+    float e = sv * sigma;      e = e * sqrt_dt;
+    float Vn = fmaf(gx, e, c);
+    Vn = (floor_kind == ORC_FLOOR_ABS) ? fabsf(Vn) : fmaxf(Vn, 0.0f);
+    *S = Sn; *V = Vn;
+}
+
+void orc_fe_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,
+                uint64_t first_path, uint64_t n_paths, int calls,
+                float *S_out, float *V_out, double *sum, double *sumsq, int threads)
+{
+    const float dt = p->T / p->N;                       /* NMCH.cu:9 */
+    const float K = p->S_0;                             /* NMCH.cu:7 */
+    const float sqrt_dt = sqrtf(dt);                    /* NMCH_FE.cu:152 */
+    const float sqrt_rho = sqrtf(1 - p->rho * p->rho);  /* NMCH_FE.cu:153 */
+    double acc = 0.0, acc2 = 0.0;
+    xorwow_build_matrices();
+    if (threads <= 0) threads = orc_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc, acc2) num_threads(threads) schedule(static)
+#endif
+    for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+        orc_rng_t st;
+        orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, 0);   /* random.cu:8-9 */
+        float St = 0, Vt = 0;
+        for (int call = 0; call < calls; ++call) {
+            St = p->S_0; Vt = p->v_0;
+            for (int n = 0; n < p->N; ++n) {
+                float gx, gy;
+                orc_normal2(&st, &gx, &gy);
+                fe_step(&St, &Vt, gx, gy, p->r, p->k, p->rho, p->theta, p->sigma, dt, sqrt_dt,
+                        sqrt_rho, floor_kind);
+            }
+        }
+        float pay = fmaxf(0.0f, St - K);                /* NMCH_FE.cu:171 */
+        acc += (double)pay;
+        acc2 += (double)pay * (double)pay;
+        if (S_out) S_out[i] = St;
+        if (V_out) V_out[i] = Vt;
+    }
+    if (sum) *sum = acc;
+    if (sumsq) *sumsq = acc2;
+}
+
+/* ======================================================================== */
+/* EM  (NMCH_EM.cu:213-260)                                                  */
+/* ======================================================================== */
+void orc_em_run(const orc_params_t *p, int rng_kind, uint64_t seed,
+                uint64_t first_path, uint64_t n_paths, int calls,
+                float *S_out, float *V_out, double *sum, double *sumsq, int threads)
+{
+    const float dt = p->T / p->N;
+    const float K = p->S_0;
+    const float k = p->k, theta = p->theta, sigma = p->sigma, rho = p->rho, v_0 = p->v_0;
+    const float exp_kdt = expf(-k * dt);                                           /* :226 */
+    const float d = 2.0f * k * theta / (sigma * sigma);                            /* :227 */
+    const float lambda_const = (2 * k * exp_kdt) / (sigma * sigma * (1 - exp_kdt)); /* :229 */
+    const float scale = sigma * sigma * (1.0f - exp_kdt) / (2.0f * k);             /* :240 */
+    double acc = 0.0, acc2 = 0.0;
+    xorwow_build_matrices();
+    if (threads <= 0) threads = orc_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc, acc2) num_threads(threads) schedule(dynamic, 64)
+#endif
+    for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+        orc_rng_t st;
+        orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, 0);
+        float St = 0, Vt = 0;
+        for (int call = 0; call < calls; ++call) {
+            Vt = v_0;
+            float vI = 0.0f;
+            for (int n = 0; n < p->N; ++n) {
+                float lambda = lambda_const * Vt;
+                int N_p = (int)orc_poisson(&st, lambda);
+                float gamma = orc_gamma(&st, d + N_p);
+                float Vt_next = scale * gamma;
+                vI += (Vt + Vt_next);
+                Vt = Vt_next;
+            }
+            vI = (float)(vI * (dt * 0.5));                    /* :247, double multiply */
+            float m = (1.0f / sigma) * (Vt - v_0 - k * theta + k * vI);   /* :249, T=1 assumed */
+            m = -0.5f * vI + rho * m;                          /* :251 */
+            float sigma2 = (1.0f - rho * rho) * vI;            /* :253 */
+            St = expf(m + sqrtf(sigma2) * orc_normal(&st));    /* :260, S_0=1, r=0 assumed */
+        }
+        float pay = fmaxf(0.0f, St - K);
+        acc += (double)pay;
+        acc2 += (double)pay * (double)pay;
+        if (S_out) S_out[i] = St;
+        if (V_out) V_out[i] = Vt;
+    }
+    if (sum) *sum = acc;
+    if (sumsq) *sumsq = acc2;
+}
+
+/* ---- scheme-level EM with exact samplers (statistical oracle) ------------ */
+static inline uint64_t splitmix64(uint64_t *x)
+{
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double sm_uniform(uint64_t *x) { return ((splitmix64(x) >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+static inline double sm_normal(uint64_t *x)
+{
+    double u = sm_uniform(x), v = sm_uniform(x);
+    return sqrt(-2.0 * log(u)) * cos(6.283185307179586 * v);
+}
+static double sm_gamma(uint64_t *x, double alpha)
+{
+    double boost = 1.0;
+    if (alpha < 1.0) { boost = pow(sm_uniform(x), 1.0 / alpha); alpha += 1.0; }
+    double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        double z, v;
+        do { z = sm_normal(x); v = 1.0 + c * z; } while (v <= 0.0);
+        v = v * v * v;
+        double u = sm_uniform(x);
+        if (log(u) < 0.5 * z * z + d * (1.0 - v + log(v))) return d * v * boost;
+    }
+}
+static unsigned sm_poisson(uint64_t *x, double lambda)
+{
+    if (lambda < 30.0) {
+        double L = exp(-lambda), p = 1.0; unsigned k = 0;
+        do { k++; p *= sm_uniform(x); } while (p > L);
+        return k - 1;
+    }
+    /* Hoermann PTRS (transformed rejection with squeeze), exact */
+    double slam = sqrt(lambda), loglam = log(lambda);
+    double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        double U = sm_uniform(x) - 0.5, V = sm_uniform(x);
+        double us = 0.5 - fabs(U);
+        double kf = floor((2.0 * a / us + b) * U + lambda + 0.43);
+        if (us >= 0.07 && V <= vr) return (unsigned)kf;
+        if (kf < 0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lambda + kf * loglam - lgamma(kf + 1.0))
+            return (unsigned)kf;
+    }
+}
+
+void orc_em_exact_run(const orc_params_t *p, uint64_t seed, uint64_t n_paths,
+                      double *sum, double *sumsq, double *sum_ST, int threads)
+{
+    const double dt = (double)p->T / p->N, k = p->k, theta = p->theta, sigma = p->sigma, rho = p->rho;
+    const double e = exp(-k * dt), om = -expm1(-k * dt);
+    const double d = 2.0 * k * theta / (sigma * sigma);
+    const double lc = 2.0 * k * e / (sigma * sigma * om), scale = sigma * sigma * om / (2.0 * k);
+    const double K = p->S_0;
+    double acc = 0, acc2 = 0, accS = 0;
+    if (threads <= 0) threads = orc_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc, acc2, accS) num_threads(threads) schedule(dynamic, 64)
+#endif
+    for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+        uint64_t x = seed * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xD1B54A32D192ED03ull;
+        double V = p->v_0, vI = 0.0;
+        for (int n = 0; n < p->N; ++n) {
+            unsigned Np = sm_poisson(&x, lc * V);
+            double Vn = scale * sm_gamma(&x, d + Np);
+            vI += V + Vn;
+            V = Vn;
+        }
+        vI *= 0.5 * dt;
+        double m = (V - p->v_0 - k * theta * p->T + k * vI) / sigma;
+        double lnS = log((double)p->S_0) + p->r * p->T - 0.5 * vI + rho * m
+                   + sqrt((1.0 - rho * rho) * vI) * sm_normal(&x);
+        double S = exp(lnS);
+        double pay = fmax(0.0, S - K);
+        acc += pay; acc2 += pay * pay; accS += S;
+    }
+    if (sum) *sum = acc;
+    if (sumsq) *sumsq = acc2;
+    if (sum_ST) *sum_ST = accS;
+}
+
+/* ======================================================================== */
+/* host statistics                                                           */
+/* ======================================================================== */
+float orc_get_err(int state_numbers, float strike_price, float price_squared)
+{   /* NMCH_FE.hpp:50-55 verbatim in meaning: 1.0f/(n-1) in float, n*E[X^2] in float */
+    float err = 1.96 * sqrt((double)(1.0f / (state_numbers - 1)) *
+                            (state_numbers * price_squared - (strike_price * strike_price))) /
+                sqrt((double)state_numbers);
+    return err;
+}
+
+double orc_NP(double x)
+{   /* utils.cu:5-25, Abramowitz-Stegun 26.2.17 */
+    const double p = 0.2316419, b1 = 0.319381530, b2 = -0.356563782, b3 = 1.781477937,
+                 b4 = -1.821255978, b5 = 1.330274429, one_over_twopi = 0.39894228;
+    double t;
+    if (x >= 0.0) {
+        t = 1.0 / (1.0 + p * x);
+        return 1.0 - one_over_twopi * exp(-x * x / 2.0) * t * (t * (t * (t * (t * b5 + b4) + b3) + b2) + b1);
+    }
+    t = 1.0 / (1.0 - p * x);
+    return one_over_twopi * exp(-x * x / 2.0) * t * (t * (t * (t * (t * b5 + b4) + b3) + b2) + b1);
+}
+
+float orc_print_true_price(float S_0, float K, float r, float sigma)
+{   /* NMCH_FE.cu:336-338 : Black-Scholes with vol:=sigma, T:=1 */
+    float real_price = S_0 * orc_NP((r + 0.5 * sigma * sigma) / sigma) -
+                       K * expf(-r) * orc_NP((r - 0.5 * sigma * sigma) / sigma);
+    return real_price;
+}
+
+/* Semi-analytic Heston call: Heston (1993) P1/P2 with the Albrecher et al.
+ * "little trap" branch choice; composite 16-point Gauss-Legendre on [0, 400]. */
+static double complex heston_cf(double phi, int j, double lnS0, double v0, double r, double kappa,
+                                double theta, double sigma, double rho, double T)
+{
+    const double u = (j == 1) ? 0.5 : -0.5;
+    const double b = (j == 1) ? kappa - rho * sigma : kappa;
+    const double a = kappa * theta;
+    double complex iphi = I * phi;
+    double complex rsi = rho * sigma * iphi;
+    double complex d = csqrt((rsi - b) * (rsi - b) - sigma * sigma * (2.0 * u * iphi - phi * phi));
+    double complex g = (b - rsi - d) / (b - rsi + d);
+    double complex edT = cexp(-d * T);
+    double complex C = r * iphi * T + a / (sigma * sigma) * ((b - rsi - d) * T - 2.0 * clog((1.0 - g * edT) / (1.0 - g)));
+    double complex D = (b - rsi - d) / (sigma * sigma) * (1.0 - edT) / (1.0 - g * edT);
+    return cexp(C + D * v0 + iphi * lnS0);
+}
+
+double orc_heston_call(double S0, double K, double v0, double r, double kappa,
+                       double theta, double sigma, double rho, double T)
+{
+    static const double gx[8] = {0.0950125098376374, 0.2816035507792589, 0.4580167776572274,
+        0.6178762444026438, 0.7554044083550030, 0.8656312023878318, 0.9445750230732326, 0.9894009349916499};
+    static const double gw[8] = {0.1894506104550685, 0.1826034150449236, 0.1691565193950025,
+        0.1495959888165767, 0.1246289712555339, 0.0951585116824928, 0.0622535239386479, 0.0271524594117541};
+    const double lnS0 = log(S0), lnK = log(K);
+    const double upper = 400.0;
+    const int panels = 4000;
+    const double h = upper / panels;
+    double I1 = 0.0, I2 = 0.0;
+    for (int pnl = 0; pnl < panels; ++pnl) {
+        double mid = (pnl + 0.5) * h, half = 0.5 * h;
+        for (int q = 0; q < 8; ++q)
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                double phi = mid + sgn * half * gx[q];
+                double complex e = cexp(-I * phi * lnK) / (I * phi);
+                I1 += gw[q] * half * creal(e * heston_cf(phi, 1, lnS0, v0, r, kappa, theta, sigma, rho, T));
+                I2 += gw[q] * half * creal(e * heston_cf(phi, 2, lnS0, v0, r, kappa, theta, sigma, rho, T));
+            }
+    }
+    double P1 = 0.5 + I1 / M_PI, P2 = 0.5 + I2 / M_PI;
+    return S0 * P1 - K * exp(-r * T) * P2;
+}
+
+/* ======================================================================== */
+/* exploration grid (exploration.cu:46-52, 71-88)                            */
+/* ======================================================================== */
+int orc_exploration_grid(int steps, int apply_filter, float *k_out, float *theta_out, float *sigma_out, int cap)
+{
+    float k_min = 0.1f, k_max = 10.0f;
+    float theta_min = 0.01f, theta_max = 0.5f;
+    float sigma_min = 0.1f, sigma_max = 1.0f;
+    float sigma_step = (sigma_max - sigma_min) / steps;
+    float theta_step = (theta_max - theta_min) / steps;
+    float k_step = (k_max - k_min) / steps;
+    int n = 0;
+    for (float sigma = sigma_min; sigma <= sigma_max; sigma += sigma_step)
+        for (float theta = theta_min; theta <= theta_max; theta += theta_step)
+            for (float k = k_min; k <= k_max; k += k_step) {
+                if (apply_filter && (20 * k * theta < sigma * sigma)) continue;
+                if (n < cap) { k_out[n] = k; theta_out[n] = theta; sigma_out[n] = sigma; }
+                ++n;
+            }
+    return n;
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
