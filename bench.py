@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Heston path-simulation hot path on N B200s (one process per GPU).
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (N>1: launched by torch.distributed.run) prints ONE
+JSON line on rank 0.  A "step" is one compute() pass of the hot path over one batch of synthetic paths:
+BASELINE.json configs[1] (FE Euler, N=1000 time steps, 2^24 paths per GPU, README parameters, seed 1234).
+Paths shard over ranks by disjoint Philox subsequences (weak scaling: 2^24 paths per GPU); one NCCL
+allreduce of the two FP64 moments per step when N>1.
+
+  value     FE: path-steps/s (EM: paths/s), whole job, inputs are 11 scalars (nothing to stage in HBM)
+  e2e       the same metric through the public C-ABI call nmch_engine_compute() with host buffers:
+            kernel-parameter upload + launch + sync + the result landing in host memory, every step
+  roofline  the FE kernel against the FP32/SFU ISSUE roofline of SURVEY.md §8d (this path moves no HBM
+            bytes and has no GEMM: neither "hbm" nor "tensor" bounds it)
+  cpu_baseline  the oracle port of the reference loop on this box's host cores (bounded sample)
+
+`--impl reference`: the reference arm.  The reference is a CUDA program with no CPU implementation; its hot
+loop restated in C (oracle/, kind "port") is timed on the host cores as the tier asks, and when the
+reference's own CUDA build (oracle/_ref/nmch_ref_harness) travelled to the box its measured throughput on
+the same GPU is attached as "reference_cuda" -- that is the like-for-like number.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+README = dict(T=1.0, S_0=1.0, v_0=0.1, r=0.0, k=0.5, rho=-0.7, theta=0.1, sigma=0.3)
+ISSUE_PER_CLK_PER_SM = min(128.0 / 42.0, 16.0 / 5.0)      # 42 thread-instr, 5 MUFU per path-step
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (NVML) sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), "power_w_max": max(self.power) if self.power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's loop, all host threads, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(method: str, N: int, budget_s: float = 12.0):
+    from oracle import oracle as o
+    p = o.Params(N=N, **README)
+    threads = o.max_threads()
+    n = 1 << 13
+    run = (lambda n: o.fe_run(p, rng=o.RNG_XORWOW, n_paths=n)) if method == "fe" else (
+        lambda n: o.em_run(p, rng=o.RNG_XORWOW, n_paths=n))
+    run(256)                                     # builds the skip-ahead tables outside the timed region
+    t0 = time.perf_counter()
+    run(n)
+    dt = time.perf_counter() - t0
+    while dt < 1.0 and n < (1 << 24):            # find the rate, then size one sample to the budget
+        n *= 4
+        t0 = time.perf_counter()
+        run(n)
+        dt = time.perf_counter() - t0
+    n_big = int(min(max(n, n * budget_s / max(dt, 1e-9)), 1 << 26))
+    n_big = max(1 << 13, 1 << (n_big.bit_length() - 1))
+    t0 = time.perf_counter()
+    run(n_big)
+    dt = time.perf_counter() - t0
+    units = n_big * N if method == "fe" else n_big
+    return {"value": units / dt, "unit": "path-steps/s" if method == "fe" else "paths/s", "cores": threads,
+            "kind": "port", "sample": f"{method.upper()} oracle (XORWOW stream incl. per-path curand_init), "
+                                      f"{n_big} paths x {N} steps, {dt:.2f} s, {threads} OpenMP threads"}
+
+
+def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3):
+    """The reference's own CUDA build (unmodified sources, nvcc -arch=sm_100) on this GPU, if shipped."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "nmch_ref_harness")
+    if not os.path.exists(exe):
+        return None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+    except Exception:
+        return None
+    out = {}
+    n = 1 << log2_paths
+    for rng in ("xorwow", "philox"):
+        try:
+            r = subprocess.run([exe, "--method", method, "--rng", rng, "--kernel", "k3", "--NTPB", "512", "--NB",
+                                str(n // 512), "--N", str(N), "--repeat", str(repeat + 1)],
+                               capture_output=True, text=True, timeout=900, check=True)
+            rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")][1:]   # drop the warm-up call
+            ms = min(x["exec_ms"] for x in rows)
+            units = n * N if method == "fe" else n
+            out[rng] = {"value": units / (ms * 1e-3), "exec_ms": ms, "init_ms": rows[0]["init_ms"],
+                        "E": rows[-1]["E"], "E2": rows[-1]["E2"]}
+        except Exception as ex:  # noqa: BLE001
+            out[rng] = {"error": str(ex)[:200]}
+    out["what"] = (f"reference NMCH_{method.upper()}_K3_MM<rng> (unmodified sources, -O3 -arch=sm_100), 512 x {n // 512} "
+                   f"paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); unit as `unit`")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--method", default="fe", choices=["fe", "em"])
+    ap.add_argument("--log2-paths", type=int, default=None, help="paths per GPU (default 24 for FE, 22 for EM)")
+    ap.add_argument("--N", type=int, default=1000)
+    ap.add_argument("--floor", default="abs", choices=["abs", "plus"])
+    ap.add_argument("--paths-per-thread", type=int, default=0)
+    ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    log2_paths = args.log2_paths if args.log2_paths is not None else (24 if args.method == "fe" else 22)
+    n_per_gpu = 1 << log2_paths
+    N = args.N
+    metric = "fe_path_steps_per_s" if args.method == "fe" else "em_paths_per_s"
+    unit = "path-steps/s" if args.method == "fe" else "paths/s"
+    units_per_gpu_step = n_per_gpu * N if args.method == "fe" else n_per_gpu
+    workload = (f"BASELINE configs[1]: FE Euler |.| floor, README params, N={N}, 2^{log2_paths} paths per GPU, seed 1234"
+                if args.method == "fe" else
+                f"BASELINE configs[2]: EM exact scheme, README params, N={N}, 2^{log2_paths} paths per GPU, seed 1234")
+    config = {"workload": workload, "method": args.method, "floor": args.floor, "n_steps": N,
+              "paths_per_gpu": n_per_gpu, "global_paths": n_per_gpu * world, "parallelism": f"paths sharded x{world}",
+              "l2": "n/a: the kernel has no HBM-resident inputs (11 scalars by value), state lives in registers"}
+
+    # ---------------------------------------------------------------- reference arm (host CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        times = []
+        base = None
+        for i in range(args.warmup + args.steps):
+            base = cpu_baseline(args.method, N, budget_s=max(2.0, 60.0 / max(1, args.steps + args.warmup)))
+            if i >= args.warmup:
+                times.append(base["value"])
+        v = sum(times) / len(times)
+        base["value"] = v
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "edo01/NMCH is CUDA-only; its hot loop restated in C (oracle/) is what runs on the host cores"}
+        if not args.no_reference_cuda:
+            line["reference_cuda"] = reference_cuda(args.method, log2_paths, N)
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+
+    from nmch_b200 import engine as E
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = E.Engine(NTPB=512, NB=(n_per_gpu * world) // 512, N=N, method=E.METHOD_FE if args.method == "fe" else E.METHOD_EM,
+                   floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, rng=E.RNG_PHILOX, device=local_rank,
+                   n_paths=n_per_gpu * world, first_path=rank * n_per_gpu, n_local=n_per_gpu,
+                   paths_per_thread=args.paths_per_thread, block_threads=args.block_threads, **README)
+    eng.init(1234)
+    moments = torch.zeros(2, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        eng.compute_async(stream.cuda_stream, moments.data_ptr())
+        if world > 1:
+            dist.all_reduce(moments)             # the path's one exchange: 16 bytes of FP64 partial moments
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.launch_info()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = eng.launch_info()["kernel_launches"] - launches0
+    result = moments.cpu().numpy()
+    ms_per_step = total_ms / args.steps
+    value = units_per_gpu_step * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public C-ABI call (host in, host out), every step
+    barrier()
+    t0 = time.perf_counter()
+    e2e_last = None
+    for _ in range(args.steps):
+        if world == 1:
+            e2e_last = eng.compute()             # nmch_engine_compute: param upload + launch + sync + host result
+        else:
+            step()
+            e2e_last = moments.cpu()             # D2H read of the reduced moments
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_gpu_step * world * args.steps / float(e2e_s.item())
+
+    if rank == 0:
+        info = eng.launch_info()
+        ck = clocks.summary()
+        n_total = n_per_gpu * world
+        mean = float(result[0]) / n_total
+        var = float(result[1]) / n_total - mean * mean
+        f_hz = (ck["sm_mhz"] or 1965) * 1e6
+        peak = info["sm_count"] * f_hz * ISSUE_PER_CLK_PER_SM
+        per_gpu = value / world
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tj):
+            try:
+                traffic = json.load(open(tj)).get(args.method)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 16,
+                    "api": "nmch_engine_compute (C ABI)" if world == 1 else "nmch_engine_compute_async + NCCL allreduce + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": ck,
+            "roofline": {"bound": "issue", "achieved": per_gpu, "peak": peak, "unit": unit, "frac": per_gpu / peak,
+                         "traffic": traffic,
+                         "model": "SURVEY.md §8d: SMs x f x min(128/42 issue, 16/5 MUFU) path-steps/s; f = median SM clock "
+                                  "sampled during the timed region; per-GPU achieved" if args.method == "fe" else
+                                  "EM has no fixed instruction budget (data-dependent samplers); FE model shown for scale",
+                         "peak_at_max_clock": info["sm_count"] * (ck["sm_max_mhz"] or 1965) * 1e6 * ISSUE_PER_CLK_PER_SM},
+            "kernel": {k: info[k] for k in ("grid_x", "grid_y", "block_threads", "paths_per_thread", "regs_per_thread", "sm_count")},
+            "result": {"E[X]": mean, "var": var, "std_error": (var / n_total) ** 0.5,
+                       "heston_semi_analytic": 0.1197325094 if args.method in ("fe", "em") else None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.method, N)
+        if not args.no_reference_cuda and world == 1:
+            line["reference_cuda"] = reference_cuda(args.method, log2_paths, N)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,112 @@
+/*
+ * nmch_b200.h -- C ABI of the B200-native Heston Monte-Carlo engine.
+ *
+ * This is the drop-in boundary between the reference's C++ method API (layer L3:
+ * nmch::methods::NMCH_FE_* / NMCH_EM_*, /root/reference/include/NMCH/methods/*.hpp) and the
+ * hand-written sm_100a kernels.  Plain pointers and sizes only; no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference).  The reference-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 (NMCH_OK) or a negative nmch_status; the caller
+ * serialises calls on one handle; distinct handles are independent.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point returns NMCH_ERR_CUDA.
+ */
+#ifndef NMCH_B200_H
+#define NMCH_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nmch_engine nmch_engine_t;
+
+typedef enum {
+    NMCH_OK = 0,
+    NMCH_ERR_ARG = -1,        /* bad argument / unsupported combination */
+    NMCH_ERR_CUDA = -2,       /* a CUDA runtime call or kernel failed (see nmch_last_error) */
+    NMCH_ERR_STATE = -3,      /* lifecycle misuse: compute before init, use after finalize */
+    NMCH_ERR_NCCL = -4
+} nmch_status;
+
+/* which scheme: FE = NMCH_FE_* (src/NMCH/methods/NMCH_FE.cu), EM = NMCH_EM_* (NMCH_EM.cu) */
+typedef enum { NMCH_METHOD_FE = 0, NMCH_METHOD_EM = 1 } nmch_method;
+/* variance floor g(.) of README.md:37-40; the reference codes only ABS (NMCH_FE.cu:162) */
+typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
+/* stream mode, selected by the reference's rnd_state template tag:
+ *   PHILOX         native counter-based Philox4x32-10 fused into the step loop, fast-math transforms
+ *                  (cuRAND counter layout, so the u32 words per (path, step) equal the reference's
+ *                  Philox instantiation; floats agree to ~2^-23 per draw)
+ *   XORWOW_COMPAT  curandStateXORWOW_t-compatible: same integer stream, same IEEE transforms and FMA
+ *                  contraction as the reference's CUDA build
+ *   PHILOX_COMPAT  curandStatePhilox4_32_10_t-compatible (reference CLI default, nmch.cu:119,130) */
+typedef enum { NMCH_RNG_PHILOX = 0, NMCH_RNG_XORWOW_COMPAT = 1, NMCH_RNG_PHILOX_COMPAT = 2 } nmch_rng;
+
+/* Replaces the constructor arguments of nmch::methods::NMCH (include/NMCH/methods/NMCH.hpp:42,
+ * src/NMCH/methods/NMCH.cu:6-10).  Zero in an "auto" field selects the default. */
+typedef struct {
+    int   NTPB, NB;                 /* logical paths n = NTPB*NB (NMCH_FE.cu:317); launch geometry is internal */
+    float T, S_0, v_0, r, k, rho, theta, sigma;
+    int   N;                        /* time steps; dt = T/N */
+    int   method, floor, rng;       /* nmch_method, nmch_floor, nmch_rng */
+    int   device;                   /* CUDA ordinal; -1 = current device */
+    unsigned long long n_paths;     /* auto(0) = NTPB*NB; lets n exceed the reference's int limit */
+    unsigned long long first_path;  /* shard: this engine simulates paths [first_path, first_path+n_local) */
+    unsigned long long n_local;     /* auto(0) = n_paths - first_path */
+    int   paths_per_thread;         /* auto(0): picked from n_local; 1, 2, 4 or 8 */
+    int   block_threads;            /* auto(0) = 256 */
+} nmch_params_t;
+
+/* Replaces the two managed floats `sum[2]` (NMCH_FE.cu:376, 544-545) with raw FP64 sums:
+ * E[X] = sum_payoff / n_paths, E[X^2] = sum_payoff_sq / n_paths. */
+typedef struct {
+    double sum_payoff;
+    double sum_payoff_sq;
+    unsigned long long n_paths;     /* paths behind the sums (n_local for a shard) */
+    float  exec_ms;                 /* kernel + sync, the span of the reference's Tim_exec (NMCH_FE.cu:523-540) */
+} nmch_moments_t;
+
+/* ctor of NMCH_FE_* / NMCH_EM_* (NMCH_FE.cu:313-318, NMCH_EM.cu:376-382) */
+int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out);
+/* init(seed) (NMCH_FE.cu:367-386): allocates device buffers, builds generator state.
+ * Philox: nothing to build (counter = path index); XORWOW: skip-ahead init kernel (random.cu:6-10). */
+int nmch_engine_init(nmch_engine_t *e, unsigned long long seed);
+/* set_k / set_theta / set_sigma (NMCH.hpp:76-80): host fields only, effective at next compute */
+int nmch_engine_set_params(nmch_engine_t *e, float k, float theta, float sigma);
+/* compute() (NMCH_FE.cu:516-546): one pass over all local paths, streams continue across calls */
+int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out);
+/* Same pass, asynchronous: enqueued on `cuda_stream` (a cudaStream_t; NULL = the engine's stream),
+ * raw sums {sum, sumsq} written to the DEVICE buffer d_moments[2] (e.g. an NCCL send buffer), no host
+ * sync, no exec_ms.  This is what the multi-GPU layer calls before its single allreduce. */
+int nmch_engine_compute_async(nmch_engine_t *e, void *cuda_stream, double *d_moments);
+/* The exploration sweep of src/NMCH/test/exploration.cu:71-88 as ONE launch: point i uses
+ * (k[i], theta[i], sigma[i]) and the stream position it would have had after i sequential compute()
+ * calls, so explore() equals n_points x { set_params; compute } bit for bit. out has n_points entries. */
+int nmch_engine_explore(nmch_engine_t *e, const float *k, const float *theta, const float *sigma,
+                        int n_points, nmch_moments_t *out);
+int nmch_engine_explore_async(nmch_engine_t *e, void *cuda_stream, const float *k, const float *theta,
+                              const float *sigma, int n_points, double *d_moments /* [2*n_points] */);
+/* Parity hook (no reference equivalent: its kernels only emit sums): runs one compute() pass and also
+ * returns the terminal S and V of local paths [0, count) into HOST arrays. */
+int nmch_engine_compute_paths(nmch_engine_t *e, float *S_out, float *V_out, unsigned long long count,
+                              nmch_moments_t *out);
+/* finalize() (NMCH_FE.cu:326-331); idempotent here (the reference double-frees) */
+int nmch_engine_finalize(nmch_engine_t *e);
+void nmch_engine_destroy(nmch_engine_t *e);
+
+/* Tim_init (NMCH_FE.cu:370-385) and launch facts for reports */
+float nmch_engine_init_ms(const nmch_engine_t *e);
+typedef struct {
+    int grid_x, grid_y, block_threads, paths_per_thread, regs_per_thread, sm_count;
+    unsigned long long kernel_launches;     /* kernels launched by this handle so far */
+} nmch_launch_info_t;
+int nmch_engine_launch_info(const nmch_engine_t *e, nmch_launch_info_t *out);
+
+const char *nmch_status_string(int status);
+const char *nmch_last_error(void);          /* thread-local detail of the last failure */
+int nmch_device_count(void);
+const char *nmch_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMCH_B200_H */

@@ -1,0 +1,197 @@
+// device_common.cuh -- Philox4x32-10, approximate-math wrappers and the FP64 payoff reduction
+// shared by the FE and EM kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nmchb {
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10.  Counter layout follows cuRAND (curand_kernel.h:1022-1037): ctr = (block_lo,
+// block_hi, path_lo, path_hi), key = seed.  The ten round keys depend only on the seed, so the
+// host expands them once and they travel in the kernel parameter block: after unrolling, every
+// key is a constant-bank operand of the LOP3 that consumes it -- no key registers, no key adds.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+struct PhiloxKeys {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+inline PhiloxKeys philox_expand_keys(unsigned long long seed)
+{
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) {
+        k.k0[i] = a;
+        k.k1[i] = b;
+        a += kPhiloxW0;
+        b += kPhiloxW1;
+    }
+    return k;
+}
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            const PhiloxKeys &K)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)kPhiloxM0 * c0;   // IMAD.WIDE.U32
+        const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];             // one LOP3
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+// ---------------------------------------------------------------------------------------
+// Single-instruction transcendental wrappers (MUFU.*).  .ftz keeps ptxas from wrapping them in
+// denormal-scaling sequences; every argument in the kernels is a normal number by construction.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sin_approx(float x)
+{
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cos_approx(float x)
+{
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// u32 -> float in [1,2) from the top 23 bits: SHF + LOP3 on the ALU pipe, no I2F (which shares the
+// 16-lane XU pipe with MUFU).  The value equals 1 + floor(x / 2^9) * 2^-23.
+__device__ __forceinline__ float bits_to_1_2(uint32_t x)
+{
+    return __uint_as_float((x >> 9) | 0x3f800000u);
+}
+
+// ---------------------------------------------------------------------------------------
+// Payoff moments: per-thread FP64 pair -> warp shuffle -> shared memory -> one FP64 partial per
+// block -> the last block of the point (atomic ticket) folds the partials in index order with
+// Kahan compensation and ONE thread writes the result.  Deterministic for a fixed launch shape.
+// Replaces blockReduceSum + 2 float atomicAdd per block (NMCH_FE.cu:85-126, 176-181).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct KahanPair {
+    double s, c;
+    __device__ __forceinline__ void add(double x)
+    {
+        const double y = x - c;
+        const double t = s + y;
+        c = (t - s) - y;
+        s = t;
+    }
+};
+
+// Called by every thread of the block.  partials: [n_points][blocks_per_point] double2.
+// Returns after the point's final result (if this was the last block) has been written to out[2*point].
+__device__ __forceinline__ void block_reduce_and_finish(double a, double b, double2 *partials,
+                                                        unsigned int *tickets, double *out, int point,
+                                                        int block_in_point, int blocks_per_point)
+{
+    __shared__ double sh_a[32];
+    __shared__ double sh_b[32];
+    __shared__ bool sh_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();                       // protects sh_* against a previous call in the same kernel
+    if (lane == 0) {
+        sh_a[warp] = a;
+        sh_b[warp] = b;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        a = (lane < nwarps) ? sh_a[lane] : 0.0;
+        b = (lane < nwarps) ? sh_b[lane] : 0.0;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            partials[(size_t)point * blocks_per_point + block_in_point] = make_double2(a, b);
+            __threadfence();
+            const unsigned int t = atomicAdd(&tickets[point], 1u);
+            sh_last = (t == (unsigned int)blocks_per_point - 1u);
+        }
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    // last block of this point: strided Kahan sums, then a fixed-order fold; thread 0 is the single writer
+    const double2 *src = partials + (size_t)point * blocks_per_point;
+    KahanPair ka{0.0, 0.0}, kb{0.0, 0.0};
+    for (int i = threadIdx.x; i < blocks_per_point; i += blockDim.x) {
+        const double2 v = __ldcg(src + i);
+        ka.add(v.x);
+        kb.add(v.y);
+    }
+    a = warp_sum(ka.s);
+    b = warp_sum(kb.s);
+    if (lane == 0) {
+        sh_a[warp] = a;
+        sh_b[warp] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        KahanPair fa{0.0, 0.0}, fb{0.0, 0.0};
+        for (int w = 0; w < nwarps; ++w) {
+            fa.add(sh_a[w]);
+            fb.add(sh_b[w]);
+        }
+        out[2 * point] = fa.s;
+        out[2 * point + 1] = fb.s;
+        tickets[point] = 0u;               // re-arm for the next launch
+    }
+}
+
+}  // namespace nmchb

@@ -1,0 +1,522 @@
+// engine.cu -- the C ABI (include/nmch_b200.h) over the sm_100a kernels.
+//
+// Host-side mirror of the reference's L2 drivers (src/NMCH/methods/NMCH_FE.cu:312-546,
+// NMCH_EM.cu:376-575): allocate, time with CUDA events, launch, read two numbers back.
+// Differences by design: one fused kernel per compute()/explore(), FP64 raw sums instead of two
+// float atomics, every CUDA call checked, finalize() idempotent, no managed memory (the result is
+// written by the kernel's single writer straight into mapped pinned host memory or into the
+// caller's device buffer).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/nmch_b200.h"
+#include "engine_internal.cuh"
+
+using namespace nmchb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+}  // namespace
+namespace nmchb {
+int engine_fail(int status, const char *what, cudaError_t err)
+{
+    char buf[512];
+    if (err != cudaSuccess)
+        std::snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(err), cudaGetErrorString(err));
+    else
+        std::snprintf(buf, sizeof buf, "%s", what);
+    g_last_error = buf;
+    return status;
+}
+}  // namespace nmchb
+namespace {
+inline int fail(int status, const char *what, cudaError_t err = cudaSuccess) { return engine_fail(status, what, err); }
+
+#define CU_TRY(call)                                                    \
+    do {                                                                \
+        cudaError_t err__ = (call);                                     \
+        if (err__ != cudaSuccess) return fail(NMCH_ERR_CUDA, #call, err__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (dev == prev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+
+namespace {
+
+bool is_pow2_or_mult(unsigned long long v, unsigned long long m) { return (v % m) == 0ull; }
+
+int pick_paths_per_thread(const nmch_engine *e)
+{
+    if (e->p.paths_per_thread > 0) return e->p.paths_per_thread;
+    // Enough warps first (>= 16 resident per SM), then ILP: each extra path per thread hides more of
+    // the dependent MUFU/FMA chain without costing occupancy (47 regs at P = 4).
+    const unsigned long long per_sm = e->n_local / (unsigned long long)(e->sm_count > 0 ? e->sm_count : 148);
+    if (per_sm >= 4096ull) return 4;
+    if (per_sm >= 2048ull) return 2;
+    return 1;
+}
+
+FePoint fold_fe_point(const nmch_params_t &p, float k, float theta, float sigma)
+{
+    const float dt = p.T / (float)p.N;                       // NMCH.cu:9
+    const float c0 = 1.17741002f;                            // sqrt(2 ln 2)
+    FePoint pt;
+    pt.va = 1.0f - k * dt;
+    pt.vb = k * theta * dt;
+    pt.vs = sigma * sqrtf(dt) * c0;
+    pt.pad = 0.0f;
+    return pt;
+}
+
+void fill_fe_launch(const nmch_engine *e, FeLaunch &L, int n_points, int blocks_per_point, int tiles_per_block)
+{
+    const nmch_params_t &p = e->p;
+    const float dt = p.T / (float)p.N;
+    const float c0 = 1.17741002f;
+    L.keys = philox_expand_keys(e->seed);
+    L.first_path = e->first_path;
+    L.n_local = e->n_local;
+    L.draw_offset = e->draw_offset;
+    L.N = p.N;
+    L.n_points = n_points;
+    L.blocks_per_point = blocks_per_point;
+    L.tiles_per_block = tiles_per_block;
+    L.S0 = p.S_0;
+    L.v0 = p.v_0;
+    L.K = p.S_0;                                             // at the money, NMCH.cu:7
+    L.crdt = 1.0f + p.r * dt;
+    L.zr = p.rho * sqrtf(dt) * c0;
+    L.zc = sqrtf(1.0f - p.rho * p.rho) * sqrtf(dt) * c0;
+    L.r = p.r;
+    L.rho = p.rho;
+    L.dt = dt;
+    L.sqrt_dt = sqrtf(dt);                                   // NMCH_FE.cu:152
+    L.sqrt_rho = sqrtf(1 - p.rho * p.rho);                   // NMCH_FE.cu:153
+    L.pt0 = fold_fe_point(p, p.k, p.theta, p.sigma);
+    L.raw0 = RawPoint{p.k, p.theta, p.sigma, 0.0f};
+}
+
+int ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, size_t point_bytes)
+{
+    const size_t need_partials = n_points * blocks_per_point;
+    if (need_partials > e->partials_cap) {
+        if (e->d_partials) cudaFree(e->d_partials);
+        e->d_partials = nullptr;
+        e->partials_cap = 0;
+        CU_TRY(cudaMalloc(&e->d_partials, need_partials * sizeof(double2)));
+        e->partials_cap = need_partials;
+    }
+    if (n_points > e->tickets_cap) {
+        if (e->d_tickets) cudaFree(e->d_tickets);
+        e->d_tickets = nullptr;
+        e->tickets_cap = 0;
+        CU_TRY(cudaMalloc(&e->d_tickets, n_points * sizeof(unsigned int)));
+        CU_TRY(cudaMemsetAsync(e->d_tickets, 0, n_points * sizeof(unsigned int), e->stream));
+        e->tickets_cap = n_points;
+    }
+    if (2 * n_points > e->out_cap) {
+        if (e->h_out) cudaFreeHost(e->h_out);
+        e->h_out = nullptr;
+        e->out_cap = 0;
+        CU_TRY(cudaHostAlloc((void **)&e->h_out, 2 * n_points * sizeof(double), cudaHostAllocMapped));
+        CU_TRY(cudaHostGetDevicePointer((void **)&e->h_out_dev, e->h_out, 0));
+        e->out_cap = 2 * n_points;
+    }
+    if (point_bytes > e->points_cap) {
+        if (e->d_points) cudaFree(e->d_points);
+        e->d_points = nullptr;
+        e->points_cap = 0;
+        CU_TRY(cudaMalloc(&e->d_points, point_bytes));
+        e->points_cap = point_bytes;
+    }
+    return NMCH_OK;
+}
+
+int ensure_sv(nmch_engine *e, size_t count)
+{
+    if (count > e->sv_cap) {
+        if (e->d_S) cudaFree(e->d_S);
+        if (e->d_V) cudaFree(e->d_V);
+        e->d_S = e->d_V = nullptr;
+        e->sv_cap = 0;
+        CU_TRY(cudaMalloc(&e->d_S, count * sizeof(float)));
+        CU_TRY(cudaMalloc(&e->d_V, count * sizeof(float)));
+        e->sv_cap = count;
+    }
+    return NMCH_OK;
+}
+
+// One launch over n_points parameter points.  k/theta/sigma are HOST arrays (nullptr => the engine's own
+// current parameters, n_points == 1).  Raw sums go to d_out (device-accessible, 2*n_points doubles).
+int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
+                  int n_points, double *d_out, float *S_out, float *V_out)
+{
+    const nmch_params_t &p = e->p;
+    const bool native = (p.rng == NMCH_RNG_PHILOX);
+    const bool own = (k == nullptr);
+    if (p.method == NMCH_METHOD_FE) {
+        FeLaunch L;
+        if (native) {
+            const int P = e->P, threads = e->threads;
+            const unsigned long long tile = (unsigned long long)P * threads;
+            const unsigned long long tiles = (e->n_local + tile - 1) / tile;
+            // keep the per-point partial list short when many points share the launch
+            int tiles_per_block = 1;
+            if (n_points > 1 && tiles > 256ull) tiles_per_block = (int)((tiles + 255ull) / 256ull);
+            const unsigned long long bpp = (tiles + tiles_per_block - 1) / tiles_per_block;
+            if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
+            fill_fe_launch(e, L, n_points, (int)bpp, tiles_per_block);
+            int rc = ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(FePoint));
+            if (rc) return rc;
+            const FePoint *d_pts = nullptr;
+            if (!own) {
+                std::vector<FePoint> pts(n_points);
+                for (int i = 0; i < n_points; ++i) pts[i] = fold_fe_point(p, k[i], theta[i], sigma[i]);
+                CU_TRY(cudaMemcpyAsync(e->d_points, pts.data(), pts.size() * sizeof(FePoint), cudaMemcpyHostToDevice, stream));
+                CU_TRY(cudaStreamSynchronize(stream));          // pts is a stack-lifetime staging buffer
+                d_pts = static_cast<const FePoint *>(e->d_points);
+            }
+            ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
+            CU_TRY(launch_fe_philox(L, p.floor, P, threads, d_pts, rb, S_out, V_out, stream, &e->kinfo));
+        } else {
+            const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
+            if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
+            fill_fe_launch(e, L, n_points, (int)bpp, 1);
+            int rc = ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(RawPoint));
+            if (rc) return rc;
+            const RawPoint *d_pts = nullptr;
+            if (!own) {
+                std::vector<RawPoint> pts(n_points);
+                for (int i = 0; i < n_points; ++i) pts[i] = RawPoint{k[i], theta[i], sigma[i], 0.0f};
+                CU_TRY(cudaMemcpyAsync(e->d_points, pts.data(), pts.size() * sizeof(RawPoint), cudaMemcpyHostToDevice, stream));
+                CU_TRY(cudaStreamSynchronize(stream));
+                d_pts = static_cast<const RawPoint *>(e->d_points);
+            }
+            ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
+            CU_TRY(launch_fe_compat(L, p.rng, p.floor, 256, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
+        }
+        e->draw_offset += 2ull * (unsigned long long)p.N * (unsigned long long)n_points;
+    } else {
+        int rc = em_launch_points(e, stream, k, theta, sigma, n_points, d_out, S_out, V_out);
+        if (rc) return rc;
+    }
+    e->launches += 1;
+    return NMCH_OK;
+}
+
+int check_ready(const nmch_engine *e)
+{
+    if (!e) return fail(NMCH_ERR_ARG, "null engine");
+    if (!e->inited) return fail(NMCH_ERR_STATE, "engine not initialised (call nmch_engine_init first, or it was finalized)");
+    return NMCH_OK;
+}
+
+void fill_moments(const nmch_engine *e, const double *src, int n_points, float ms, nmch_moments_t *out)
+{
+    for (int i = 0; i < n_points; ++i) {
+        out[i].sum_payoff = src[2 * i];
+        out[i].sum_payoff_sq = src[2 * i + 1];
+        out[i].n_paths = e->n_local;
+        out[i].exec_ms = ms;
+    }
+}
+
+}  // namespace
+
+// em_kernels.cu needs these engine internals
+namespace nmchb {
+int engine_ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, size_t point_bytes)
+{
+    return ensure_buffers(e, n_points, blocks_per_point, point_bytes);
+}
+}  // namespace nmchb
+
+extern "C" {
+
+int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
+{
+    if (!params || !out) return fail(NMCH_ERR_ARG, "null argument");
+    const nmch_params_t &p = *params;
+    if (p.N <= 0) return fail(NMCH_ERR_ARG, "N must be positive");
+    if (p.method != NMCH_METHOD_FE && p.method != NMCH_METHOD_EM) return fail(NMCH_ERR_ARG, "unknown method");
+    if (p.floor != NMCH_FLOOR_ABS && p.floor != NMCH_FLOOR_PLUS) return fail(NMCH_ERR_ARG, "unknown floor");
+    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_PHILOX_COMPAT) return fail(NMCH_ERR_ARG, "unknown rng mode");
+    unsigned long long n = p.n_paths;
+    if (n == 0) {
+        if (p.NTPB <= 0 || p.NB <= 0) return fail(NMCH_ERR_ARG, "NTPB and NB must be positive");
+        n = (unsigned long long)p.NTPB * (unsigned long long)p.NB;
+    }
+    if (p.first_path > n) return fail(NMCH_ERR_ARG, "first_path beyond n_paths");
+    unsigned long long n_local = p.n_local ? p.n_local : n - p.first_path;
+    if (n_local == 0 || p.first_path + n_local > n) return fail(NMCH_ERR_ARG, "empty or out-of-range shard");
+    if (p.rng == NMCH_RNG_PHILOX && !is_pow2_or_mult(p.first_path, kMaxTilePaths))
+        return fail(NMCH_ERR_ARG, "native Philox mode needs first_path to be a multiple of 4096");
+    if (p.paths_per_thread != 0 && p.paths_per_thread != 1 && p.paths_per_thread != 2 && p.paths_per_thread != 4 &&
+        p.paths_per_thread != 8)
+        return fail(NMCH_ERR_ARG, "paths_per_thread must be 0 (auto), 1, 2, 4 or 8");
+    if (p.block_threads != 0 && p.block_threads != 128 && p.block_threads != 256)
+        return fail(NMCH_ERR_ARG, "block_threads must be 0 (auto), 128 or 256");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(NMCH_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    int dev = p.device;
+    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(NMCH_ERR_ARG, "device ordinal out of range");
+    nmch_engine *e = new (std::nothrow) nmch_engine();
+    if (!e) return fail(NMCH_ERR_ARG, "out of host memory");
+    e->p = p;
+    e->device = dev;
+    e->n_paths = n;
+    e->first_path = p.first_path;
+    e->n_local = n_local;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return NMCH_OK;
+}
+
+int nmch_engine_init(nmch_engine_t *e, unsigned long long seed)
+{
+    if (!e) return fail(NMCH_ERR_ARG, "null engine");
+    if (e->inited) return fail(NMCH_ERR_STATE, "engine already initialised");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&e->ev0));
+    CU_TRY(cudaEventCreate(&e->ev1));
+    CU_TRY(cudaEventRecord(e->ev0, e->stream));
+    e->seed = seed;
+    e->draw_offset = 0;
+    e->em_calls = 0;
+    e->threads = e->p.block_threads ? e->p.block_threads : 256;
+    e->P = pick_paths_per_thread(e);
+    if (e->p.rng == NMCH_RNG_XORWOW_COMPAT) {
+        const size_t n = (size_t)e->n_local;
+        CU_TRY(xorwow_tables_create(&e->xtab));
+        uint32_t *base = nullptr;
+        CU_TRY(cudaMalloc(&base, 6 * n * sizeof(uint32_t)));
+        e->xs.d = base; e->xs.v0 = base + n; e->xs.v1 = base + 2 * n;
+        e->xs.v2 = base + 3 * n; e->xs.v3 = base + 4 * n; e->xs.v4 = base + 5 * n;
+        if (e->p.method == NMCH_METHOD_EM) {
+            CU_TRY(cudaMalloc(&e->xs.bm_flag, n * sizeof(int)));
+            CU_TRY(cudaMalloc(&e->xs.bm_extra, n * sizeof(float)));
+            CU_TRY(cudaMalloc(&e->xs.bm_flag_d, n * sizeof(int)));
+            CU_TRY(cudaMalloc(&e->xs.bm_extra_d, n * sizeof(double)));
+        }
+        CU_TRY(launch_xorwow_init(e->xtab, seed, e->first_path, e->n_local, e->xs, e->stream));
+        e->launches += 1;
+    } else if (e->p.rng == NMCH_RNG_PHILOX_COMPAT && e->p.method == NMCH_METHOD_EM) {
+        int rc = em_philox_compat_init(e);
+        if (rc) return rc;
+    }
+    int rc = ensure_buffers(e, 1, 1, 0);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev1, e->stream));
+    CU_TRY(cudaEventSynchronize(e->ev1));
+    CU_TRY(cudaEventElapsedTime(&e->init_ms, e->ev0, e->ev1));
+    e->inited = true;
+    return NMCH_OK;
+}
+
+int nmch_engine_set_params(nmch_engine_t *e, float k, float theta, float sigma)
+{
+    if (!e) return fail(NMCH_ERR_ARG, "null engine");
+    e->p.k = k;
+    e->p.theta = theta;
+    e->p.sigma = sigma;
+    return NMCH_OK;
+}
+
+int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!out) return fail(NMCH_ERR_ARG, "null output");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    rc = ensure_buffers(e, 1, 1, 0);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = launch_points(e, e->stream, nullptr, nullptr, nullptr, 1, e->h_out_dev, nullptr, nullptr);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev1, e->stream));
+    CU_TRY(cudaEventSynchronize(e->ev1));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    fill_moments(e, e->h_out, 1, ms, out);
+    return NMCH_OK;
+}
+
+int nmch_engine_compute_async(nmch_engine_t *e, void *cuda_stream, double *d_moments)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!d_moments) return fail(NMCH_ERR_ARG, "null device output");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream;
+    return launch_points(e, s, nullptr, nullptr, nullptr, 1, d_moments, nullptr, nullptr);
+}
+
+int nmch_engine_explore(nmch_engine_t *e, const float *k, const float *theta, const float *sigma, int n_points,
+                        nmch_moments_t *out)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!k || !theta || !sigma || !out || n_points <= 0) return fail(NMCH_ERR_ARG, "bad exploration arguments");
+    if (n_points > 65535) return fail(NMCH_ERR_ARG, "at most 65535 points per launch");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    rc = ensure_buffers(e, n_points, 1, 0);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = launch_points(e, e->stream, k, theta, sigma, n_points, e->h_out_dev, nullptr, nullptr);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev1, e->stream));
+    CU_TRY(cudaEventSynchronize(e->ev1));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    fill_moments(e, e->h_out, n_points, ms, out);
+    return NMCH_OK;
+}
+
+int nmch_engine_explore_async(nmch_engine_t *e, void *cuda_stream, const float *k, const float *theta,
+                              const float *sigma, int n_points, double *d_moments)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!k || !theta || !sigma || !d_moments || n_points <= 0) return fail(NMCH_ERR_ARG, "bad exploration arguments");
+    if (n_points > 65535) return fail(NMCH_ERR_ARG, "at most 65535 points per launch");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream;
+    return launch_points(e, s, k, theta, sigma, n_points, d_moments, nullptr, nullptr);
+}
+
+int nmch_engine_compute_paths(nmch_engine_t *e, float *S_out, float *V_out, unsigned long long count,
+                              nmch_moments_t *out)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!S_out || !V_out || !out) return fail(NMCH_ERR_ARG, "null output");
+    if (count > e->n_local) return fail(NMCH_ERR_ARG, "count exceeds the local path count");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    rc = ensure_sv(e, (size_t)e->n_local);
+    if (rc) return rc;
+    rc = ensure_buffers(e, 1, 1, 0);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = launch_points(e, e->stream, nullptr, nullptr, nullptr, 1, e->h_out_dev, e->d_S, e->d_V);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev1, e->stream));
+    CU_TRY(cudaMemcpyAsync(S_out, e->d_S, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(V_out, e->d_V, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    fill_moments(e, e->h_out, 1, ms, out);
+    return NMCH_OK;
+}
+
+int nmch_engine_finalize(nmch_engine_t *e)
+{
+    if (!e) return fail(NMCH_ERR_ARG, "null engine");
+    if (!e->inited) return NMCH_OK;                      // idempotent (the reference double-frees)
+    DeviceGuard guard(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->d_partials) cudaFree(e->d_partials);
+    if (e->d_tickets) cudaFree(e->d_tickets);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->d_points) cudaFree(e->d_points);
+    if (e->d_S) cudaFree(e->d_S);
+    if (e->d_V) cudaFree(e->d_V);
+    if (e->xs.d) cudaFree(e->xs.d);
+    if (e->xs.bm_flag) cudaFree(e->xs.bm_flag);
+    if (e->xs.bm_extra) cudaFree(e->xs.bm_extra);
+    if (e->xs.bm_flag_d) cudaFree(e->xs.bm_flag_d);
+    if (e->xs.bm_extra_d) cudaFree(e->xs.bm_extra_d);
+    em_release(e);
+    xorwow_tables_destroy(e->xtab);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    e->d_partials = nullptr; e->partials_cap = 0;
+    e->d_tickets = nullptr; e->tickets_cap = 0;
+    e->h_out = e->h_out_dev = nullptr; e->out_cap = 0;
+    e->d_points = nullptr; e->points_cap = 0;
+    e->d_S = e->d_V = nullptr; e->sv_cap = 0;
+    e->xs = XorwowState{};
+    e->xtab = nullptr;
+    e->ev0 = e->ev1 = nullptr;
+    e->stream = nullptr;
+    e->inited = false;
+    return NMCH_OK;
+}
+
+void nmch_engine_destroy(nmch_engine_t *e)
+{
+    if (!e) return;
+    nmch_engine_finalize(e);
+    delete e;
+}
+
+float nmch_engine_init_ms(const nmch_engine_t *e) { return e ? e->init_ms : 0.0f; }
+
+int nmch_engine_launch_info(const nmch_engine_t *e, nmch_launch_info_t *out)
+{
+    if (!e || !out) return fail(NMCH_ERR_ARG, "null argument");
+    out->grid_x = e->kinfo.grid_x;
+    out->grid_y = e->kinfo.grid_y;
+    out->block_threads = e->kinfo.block_threads;
+    out->paths_per_thread = e->kinfo.paths_per_thread;
+    out->regs_per_thread = e->kinfo.regs_per_thread;
+    out->sm_count = e->sm_count;
+    out->kernel_launches = e->launches;
+    return NMCH_OK;
+}
+
+const char *nmch_status_string(int status)
+{
+    switch (status) {
+    case NMCH_OK: return "ok";
+    case NMCH_ERR_ARG: return "invalid argument";
+    case NMCH_ERR_CUDA: return "CUDA error";
+    case NMCH_ERR_STATE: return "invalid engine state";
+    case NMCH_ERR_NCCL: return "NCCL error";
+    default: return "unknown status";
+    }
+}
+
+const char *nmch_last_error(void) { return g_last_error.c_str(); }
+
+int nmch_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *nmch_version(void) { return "nmch_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// engine_internal.cuh -- the engine object behind the opaque nmch_engine_t handle, shared by engine.cu
+// (FE + lifecycle) and em_kernels.cu (EM launches).
+#pragma once
+#include "../../include/nmch_b200.h"
+#include "kernels.cuh"
+
+struct nmch_engine {
+    nmch_params_t p{};
+    int device = 0;
+    int sm_count = 0;
+    bool inited = false;
+    unsigned long long seed = 0;
+    unsigned long long n_paths = 0, first_path = 0, n_local = 0;
+    unsigned long long draw_offset = 0;      // FE Philox modes: u32 words consumed per path so far
+    unsigned long long em_calls = 0;         // EM native mode: compute() calls so far (selects a fresh stream)
+    float init_ms = 0.0f;
+    int P = 4, threads = 256;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // reduction buffers
+    double2 *d_partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int *d_tickets = nullptr;
+    size_t tickets_cap = 0;
+    double *h_out = nullptr;                 // mapped pinned host memory, written by the kernel
+    double *h_out_dev = nullptr;             // its device alias
+    size_t out_cap = 0;
+    void *d_points = nullptr;                // FePoint[] / RawPoint[] / EmPoint[]
+    size_t points_cap = 0;
+    float *d_S = nullptr, *d_V = nullptr;    // parity hook buffers
+    size_t sv_cap = 0;
+    // XORWOW-compat state
+    nmchb::XorwowSkipTables *xtab = nullptr;
+    nmchb::XorwowState xs{};
+    nmchb::KernelInfo kinfo{};
+    unsigned long long launches = 0;
+};
+
+namespace nmchb {
+
+int engine_fail(int status, const char *what, cudaError_t err = cudaSuccess);
+int engine_ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, size_t point_bytes);
+
+// em_kernels.cu
+int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
+                     int n_points, double *d_out, float *S_out, float *V_out);
+int em_philox_compat_init(nmch_engine *e);
+void em_release(nmch_engine *e);
+
+}  // namespace nmchb

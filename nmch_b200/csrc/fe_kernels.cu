@@ -1,0 +1,325 @@
+// fe_kernels.cu -- forward-Euler Heston path kernels for sm_100a.
+//
+// Replaces FE_k1 / FE_k2 / FE_k2_philox / FE_k3 of the reference (src/NMCH/methods/NMCH_FE.cu:16-304)
+// with ONE native kernel (fe_philox_kernel) plus a validation kernel (fe_compat_kernel) that
+// reproduces the reference's cuRAND streams and IEEE arithmetic draw for draw.
+//
+// Native kernel, per path-step (see DESIGN.md §Kernels for the instruction budget):
+//   * half a Philox4x32-10 block (the block serves two steps; round keys are constant-bank operands)
+//   * u32 -> float by bit splicing (ALU pipe, no I2F on the XU pipe)
+//   * Box-Muller with MUFU.LG2 / MUFU.SIN / MUFU.COS and ONE MUFU.SQRT shared with the SDE:
+//       sqrt(V)*sqrt(-2 ln u) = c0 * sqrt(-V * lg2 u),  c0 = sqrt(2 ln 2) folded into host constants
+//   * S' = S * (1 + r dt + q sin * zr + q cos * zc),  V' = g(V*va + vb + q sin * vs)
+//   state (S, V, counters) stays in registers for all N steps: zero HBM traffic in the loop.
+#include "kernels.cuh"
+
+namespace nmchb {
+
+// ------------------------------------------------------------------------------------------
+// native Philox kernel
+// ------------------------------------------------------------------------------------------
+template <int FLOOR>
+__device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, uint32_t wb, float crdt,
+                                               float zr, float zc, const FePoint &pc)
+{
+    const float f1 = bits_to_1_2(wa);
+    const float f2 = bits_to_1_2(wb);
+    const float u = f1 - 0.99999994f;                 // (floor(wa/2^9) + 0.5) * 2^-23, in (0,1): exact
+    const float l2 = lg2_approx(u);                   // < 0
+    const float q = sqrt_approx(-(V * l2));           // sqrt(V) * sqrt(-lg2 u)
+    const float ang = f2 * 6.2831855f;                // [2pi, 4pi): same sine/cosine as [0, 2pi)
+    const float gs = q * sin_approx(ang);
+    const float gc = q * cos_approx(ang);
+    float m = fmaf(gs, zr, crdt);
+    m = fmaf(gc, zc, m);
+    S *= m;
+    float vn = fmaf(V, pc.va, pc.vb);
+    vn = fmaf(gs, pc.vs, vn);
+    V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
+}
+
+template <int P, int FLOOR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ pts, ReduceBuffers rb,
+                 float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    constexpr int TILE = P * THREADS;
+    const int point = blockIdx.y;
+    const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
+    const float crdt = L.crdt, zr = L.zr, zc = L.zc;
+
+    // stream position of this point: what `point` sequential compute() calls would have consumed
+    const unsigned long long w0 = L.draw_offset + (unsigned long long)point * 2ull * (unsigned long long)L.N;
+    const bool half_start = (w0 & 2ull) != 0ull;
+
+    double acc = 0.0, acc2 = 0.0;
+    for (int t = 0; t < L.tiles_per_block; ++t) {
+        const unsigned long long tile = (unsigned long long)blockIdx.x * L.tiles_per_block + t;
+        const unsigned long long local0 = tile * TILE;
+        if (local0 >= L.n_local) break;
+        const unsigned long long g0 = L.first_path + local0;     // multiple of TILE: no carry below
+        const uint32_t path_hi = (uint32_t)(g0 >> 32);
+        const uint32_t path_lo0 = (uint32_t)g0 + threadIdx.x;
+
+        float S[P], V[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            S[j] = L.S0;
+            V[j] = L.v0;
+        }
+        unsigned long long blk = w0 >> 2;
+        int n = L.N;
+        if (half_start && n > 0) {                                // resume in the middle of a block
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
+                fe_step_native<FLOOR>(S[j], V[j], w.z, w.w, crdt, zr, zc, pc);
+            }
+            ++blk;
+            --n;
+        }
+        const int pairs = n >> 1;
+#pragma unroll 1
+        for (int it = 0; it < pairs; ++it) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
+                fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
+                fe_step_native<FLOOR>(S[j], V[j], w.z, w.w, crdt, zr, zc, pc);
+            }
+            ++blk;
+        }
+        if (n & 1) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
+                fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const unsigned long long idx = local0 + (unsigned long long)(j * THREADS) + threadIdx.x;
+            if (idx < L.n_local) {
+                const double pay = (double)fmaxf(0.0f, S[j] - L.K);
+                acc += pay;
+                acc2 += pay * pay;
+                if (S_out != nullptr && point == L.n_points - 1) {
+                    S_out[idx] = S[j];
+                    V_out[idx] = V[j];
+                }
+            }
+        }
+    }
+    block_reduce_and_finish(acc, acc2, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+}
+
+template <int P, int FLOOR>
+static cudaError_t launch_philox_t(const FeLaunch &L, int block_threads, const FePoint *d_pts,
+                                   ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream,
+                                   KernelInfo *info)
+{
+    dim3 grid((unsigned)L.blocks_per_point, (unsigned)L.n_points, 1);
+    cudaFuncAttributes attr{};
+    cudaError_t err;
+    if (block_threads == 128) {
+        fe_philox_kernel<P, FLOOR, 128><<<grid, 128, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_philox_kernel<P, FLOOR, 128>);
+    } else {
+        fe_philox_kernel<P, FLOOR, 256><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_philox_kernel<P, FLOOR, 256>);
+    }
+    if (info) {
+        info->grid_x = (int)grid.x;
+        info->grid_y = (int)grid.y;
+        info->block_threads = block_threads == 128 ? 128 : 256;
+        info->paths_per_thread = P;
+        info->regs_per_thread = attr.numRegs;
+    }
+    const cudaError_t lerr = cudaGetLastError();
+    return lerr != cudaSuccess ? lerr : err;
+}
+
+cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int P, int block_threads, const FePoint *d_pts,
+                             ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
+{
+#define NMCHB_DISPATCH(PP)                                                                                   \
+    case PP:                                                                                                 \
+        return floor_kind == kFloorAbs                                                                       \
+                   ? launch_philox_t<PP, kFloorAbs>(L, block_threads, d_pts, rb, S_out, V_out, stream, info) \
+                   : launch_philox_t<PP, kFloorPlus>(L, block_threads, d_pts, rb, S_out, V_out, stream, info);
+    switch (P) {
+        NMCHB_DISPATCH(1)
+        NMCHB_DISPATCH(2)
+        NMCHB_DISPATCH(4)
+        NMCHB_DISPATCH(8)
+    default:
+        return cudaErrorInvalidValue;
+    }
+#undef NMCHB_DISPATCH
+}
+
+// ------------------------------------------------------------------------------------------
+// compat kernel: the reference's streams and arithmetic, one path per thread.
+// ------------------------------------------------------------------------------------------
+struct CompatXorwow {
+    uint32_t d, v0, v1, v2, v3, v4;
+    __device__ __forceinline__ uint32_t next()
+    {   // XORWOW step (published algorithm; cuRAND curand_kernel.h:863-874)
+        const uint32_t t = v0 ^ (v0 >> 2);
+        v0 = v1; v1 = v2; v2 = v3; v3 = v4;
+        v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
+        d += 362437u;
+        return v4 + d;
+    }
+};
+
+struct CompatPhilox {                    // sequential view of the counter stream, always at an even position
+    unsigned long long pos;              // next u32 word
+    uint32_t path_lo, path_hi;
+    U4 cur;
+    __device__ __forceinline__ void start(unsigned long long p, uint32_t lo, uint32_t hi, const PhiloxKeys &K)
+    {
+        pos = p; path_lo = lo; path_hi = hi;
+        const unsigned long long b = pos >> 2;
+        cur = philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), path_lo, path_hi, K);
+    }
+    __device__ __forceinline__ void next2(uint32_t &a, uint32_t &b, const PhiloxKeys &K)
+    {
+        if (pos & 2ull) {
+            a = cur.z; b = cur.w;
+            pos += 2;
+            const unsigned long long blk = pos >> 2;
+            cur = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo, path_hi, K);
+        } else {
+            a = cur.x; b = cur.y;
+            pos += 2;
+        }
+    }
+};
+
+// cuRAND's Box-Muller (curand_normal.h:70-87): IEEE logf/sqrtf, fast __sincosf, x pairs with sin.
+__device__ __forceinline__ void box_muller_compat(uint32_t x, uint32_t y, float &gx, float &gy)
+{
+    const float u = __fmaf_rn((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+    const float v = __fmaf_rn((float)y, 2.3283064e-10f * 6.2831855f, (2.3283064e-10f * 6.2831855f) / 2.0f);
+    const float s = sqrtf(__fmul_rn(-2.0f, logf(u)));
+    float sn, cs;
+    __sincosf(v, &sn, &cs);
+    gx = __fmul_rn(sn, s);
+    gy = __fmul_rn(cs, s);
+}
+
+// The reference's update (NMCH_FE.cu:160-162) with the FMA contraction nvcc applies to that source text
+// (SURVEY.md Appendix B), pinned with explicit intrinsics so it cannot drift.
+template <int FLOOR>
+__device__ __forceinline__ void fe_step_compat(float &S, float &V, float gx, float gy, float r, float k,
+                                               float rho, float theta, float sigma, float dt, float sqrt_dt,
+                                               float sqrt_rho)
+{
+    const float sv = __fsqrt_rn(V);
+    float a = __fmul_rn(r, S);
+    a = __fmaf_rn(a, dt, S);
+    float z = __fmul_rn(gy, sqrt_rho);
+    z = __fmaf_rn(gx, rho, z);
+    float b = __fmul_rn(sv, S);
+    b = __fmul_rn(b, sqrt_dt);
+    const float Sn = __fmaf_rn(b, z, a);
+    float c = __fsub_rn(theta, V);
+    c = __fmul_rn(c, k);
+    c = __fmaf_rn(c, dt, V);
+    float e = __fmul_rn(sv, sigma);
+    e = __fmul_rn(e, sqrt_dt);
+    const float Vn = __fmaf_rn(gx, e, c);
+    S = Sn;
+    V = (FLOOR == kFloorAbs) ? fabsf(Vn) : fmaxf(Vn, 0.0f);
+}
+
+template <int RNG, int FLOOR>
+__global__ void __launch_bounds__(256)
+fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict__ pts, XorwowState xs,
+                 ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < L.n_local;
+    CompatXorwow xw{};
+    CompatPhilox ph{};
+    if (valid) {
+        if (RNG == kRngXorwowCompat) {
+            xw.d = xs.d[idx]; xw.v0 = xs.v0[idx]; xw.v1 = xs.v1[idx];
+            xw.v2 = xs.v2[idx]; xw.v3 = xs.v3[idx]; xw.v4 = xs.v4[idx];
+        } else {
+            const unsigned long long g = L.first_path + idx;
+            ph.start(L.draw_offset, (uint32_t)g, (uint32_t)(g >> 32), L.keys);
+        }
+    }
+    for (int point = 0; point < L.n_points; ++point) {
+        const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
+        float S = L.S0, V = L.v0;
+        if (valid) {
+            for (int n = 0; n < L.N; ++n) {
+                uint32_t a, b;
+                if (RNG == kRngXorwowCompat) {
+                    a = xw.next();
+                    b = xw.next();
+                } else {
+                    ph.next2(a, b, L.keys);
+                }
+                float gx, gy;
+                box_muller_compat(a, b, gx, gy);
+                fe_step_compat<FLOOR>(S, V, gx, gy, L.r, rp.k, L.rho, rp.theta, rp.sigma, L.dt, L.sqrt_dt,
+                                      L.sqrt_rho);
+            }
+        }
+        double pay = 0.0;
+        if (valid) {
+            pay = (double)fmaxf(0.0f, S - L.K);
+            if (S_out != nullptr && point == L.n_points - 1) {
+                S_out[idx] = S;
+                V_out[idx] = V;
+            }
+        }
+        block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x,
+                                L.blocks_per_point);
+    }
+    if (valid && RNG == kRngXorwowCompat) {      // streams continue across compute() calls (NMCH_FE.cu:303)
+        xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;
+        xs.v2[idx] = xw.v2; xs.v3[idx] = xw.v3; xs.v4[idx] = xw.v4;
+    }
+}
+
+cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind, int block_threads,
+                             const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out, float *V_out,
+                             cudaStream_t stream, KernelInfo *info)
+{
+    (void)block_threads;
+    const int threads = 256;
+    dim3 grid((unsigned)L.blocks_per_point, 1, 1);
+    cudaFuncAttributes attr{};
+    cudaError_t err = cudaSuccess;
+#define NMCHB_COMPAT(R, F)                                                                      \
+    do {                                                                                        \
+        fe_compat_kernel<R, F><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);   \
+        err = cudaFuncGetAttributes(&attr, fe_compat_kernel<R, F>);                             \
+    } while (0)
+    if (rng_kind == kRngXorwowCompat) {
+        if (floor_kind == kFloorAbs) NMCHB_COMPAT(kRngXorwowCompat, kFloorAbs);
+        else NMCHB_COMPAT(kRngXorwowCompat, kFloorPlus);
+    } else if (rng_kind == kRngPhiloxCompat) {
+        if (floor_kind == kFloorAbs) NMCHB_COMPAT(kRngPhiloxCompat, kFloorAbs);
+        else NMCHB_COMPAT(kRngPhiloxCompat, kFloorPlus);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+#undef NMCHB_COMPAT
+    if (info) {
+        info->grid_x = (int)grid.x;
+        info->grid_y = 1;
+        info->block_threads = threads;
+        info->paths_per_thread = 1;
+        info->regs_per_thread = attr.numRegs;
+    }
+    const cudaError_t lerr = cudaGetLastError();
+    return lerr != cudaSuccess ? lerr : err;
+}
+
+}  // namespace nmchb

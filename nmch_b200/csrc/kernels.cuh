@@ -1,0 +1,78 @@
+// kernels.cuh -- launch-parameter blocks and launcher prototypes shared by the engine and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+
+namespace nmchb {
+
+constexpr int kFloorAbs = 0, kFloorPlus = 1;
+constexpr int kRngPhilox = 0, kRngXorwowCompat = 1, kRngPhiloxCompat = 2;
+constexpr int kMaxTilePaths = 4096;     // native mode: first_path % kMaxTilePaths == 0 (no carry inside a tile)
+
+// Per-point constants of the native FE kernel, folded on the host (fold_fe_point):
+//   V' = g( V*va + vb + (sqrt(V)*n1)*vs ),  va = 1-k*dt, vb = k*theta*dt, vs = sigma*sqrt(dt)*sqrt(2 ln 2)
+struct FePoint {
+    float va, vb, vs, pad;
+};
+
+// Per-point raw parameters for the compat kernels (they evaluate the reference's expressions verbatim).
+struct RawPoint {
+    float k, theta, sigma, pad;
+};
+
+struct FeLaunch {
+    PhiloxKeys keys;                    // expanded from the seed
+    unsigned long long first_path;      // global index of local path 0 (= Philox subsequence of path 0)
+    unsigned long long n_local;         // paths simulated by this engine
+    unsigned long long draw_offset;     // u32 words each path has already consumed (stream position of point 0)
+    int   N;                            // time steps
+    int   n_points;
+    int   blocks_per_point;
+    int   tiles_per_block;
+    float S0, v0, K;
+    float crdt;                         // 1 + r*dt
+    float zr, zc;                       // rho*sqrt(dt)*c0, sqrt(1-rho^2)*sqrt(dt)*c0, c0 = sqrt(2 ln 2)
+    // compat kernels: the reference's own scalars (NMCH_FE.cu:135-153)
+    float r, rho, dt, sqrt_dt, sqrt_rho;
+    FePoint  pt0;                       // used when n_points == 1 (no parameter upload)
+    RawPoint raw0;
+};
+
+struct ReduceBuffers {
+    double2      *partials;             // [n_points][blocks_per_point]
+    unsigned int *tickets;              // [n_points], zero between launches
+    double       *out;                  // [2*n_points] raw sums (device memory or mapped pinned host memory)
+};
+
+struct XorwowState {                    // structure of arrays, one entry per local path
+    uint32_t *d, *v0, *v1, *v2, *v3, *v4;
+    // Box-Muller caches used only by EM (curand_normal.h:313-326, 581-596)
+    int *bm_flag;
+    float *bm_extra;
+    int *bm_flag_d;
+    double *bm_extra_d;
+};
+
+struct KernelInfo {
+    int grid_x, grid_y, block_threads, paths_per_thread, regs_per_thread;
+};
+
+// fe_kernels.cu
+cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int paths_per_thread, int block_threads,
+                             const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out,
+                             cudaStream_t stream, KernelInfo *info);
+cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind, int block_threads,
+                             const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out,
+                             float *V_out, cudaStream_t stream, KernelInfo *info);
+
+// xorwow.cu
+struct XorwowSkipTables;                // device tables M_m^q, q = 1..3, m = 0..31
+cudaError_t xorwow_tables_create(XorwowSkipTables **out);
+void        xorwow_tables_destroy(XorwowSkipTables *t);
+cudaError_t launch_xorwow_init(const XorwowSkipTables *t, unsigned long long seed,
+                               unsigned long long first_path, unsigned long long n_local, XorwowState xs,
+                               cudaStream_t stream);
+
+}  // namespace nmchb

@@ -1,0 +1,159 @@
+// xorwow.cu -- builds per-path XORWOW generator state compatible with cuRAND's
+// curand_init(seed, subsequence = global path index, offset = 0) (reference: src/NMCH/random/random.cu:6-10).
+//
+// cuRAND ships its skip-ahead matrices as tables; this engine derives them from the generator's
+// definition: the five-word xorshift part of XORWOW is linear over GF(2), so advancing by 2^67 draws is
+// the 160x160 bit matrix T^(2^67) (67 squarings of the one-step matrix T), and digit m of the
+// subsequence in base 4 applies (T^(2^67))^(4^m) q times.  We store the q = 1, 2, 3 powers per digit so
+// a digit costs at most one vector-matrix product instead of up to three.
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace nmchb {
+
+namespace {
+
+constexpr int kDigits = 32;            // 64-bit subsequence, 2 bits per digit
+constexpr int kRowWords = 8;           // 5 state words padded to 32 bytes: two 16-byte loads per row
+
+struct Gf2Mat {
+    uint32_t row[160][5];              // row b = image of unit vector e_b
+};
+
+void host_step(uint32_t v[5])
+{
+    const uint32_t t = v[0] ^ (v[0] >> 2);
+    v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+    v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+}
+
+void host_vecmat(const uint32_t v[5], const Gf2Mat &M, uint32_t out[5])
+{
+    uint32_t r[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < 160; ++b)
+        if (v[b >> 5] >> (b & 31) & 1u)
+            for (int k = 0; k < 5; ++k) r[k] ^= M.row[b][k];
+    std::memcpy(out, r, sizeof r);
+}
+
+void host_matmul(const Gf2Mat &A, const Gf2Mat &B, Gf2Mat &out)   // out = A*B (apply A, then B)
+{
+    Gf2Mat tmp;
+    for (int b = 0; b < 160; ++b) host_vecmat(A.row[b], B, tmp.row[b]);
+    out = tmp;
+}
+
+}  // namespace
+
+struct XorwowSkipTables {
+    uint32_t *d_tables = nullptr;      // [kDigits][3][160][kRowWords]
+};
+
+static const std::vector<uint32_t> &host_tables()
+{
+    static std::vector<uint32_t> host;
+    static std::once_flag once;
+    std::call_once(once, [] {
+    Gf2Mat cur;
+    for (int b = 0; b < 160; ++b) {
+        uint32_t e[5] = {0, 0, 0, 0, 0};
+        e[b >> 5] = 1u << (b & 31);
+        host_step(e);
+        std::memcpy(cur.row[b], e, sizeof e);
+    }
+    for (int s = 0; s < 67; ++s) host_matmul(cur, cur, cur);           // T^(2^67)
+    host.assign((size_t)kDigits * 3 * 160 * kRowWords, 0u);
+    for (int m = 0; m < kDigits; ++m) {
+        Gf2Mat p2, p3;
+        host_matmul(cur, cur, p2);
+        host_matmul(p2, cur, p3);
+        const Gf2Mat *pw[3] = {&cur, &p2, &p3};
+        for (int q = 0; q < 3; ++q)
+            for (int b = 0; b < 160; ++b)
+                std::memcpy(&host[(((size_t)m * 3 + q) * 160 + b) * kRowWords], pw[q]->row[b], 5 * sizeof(uint32_t));
+        host_matmul(p2, p2, cur);                                      // next digit: fourth power
+    }
+    });
+    return host;
+}
+
+cudaError_t xorwow_tables_create(XorwowSkipTables **out)
+{
+    const std::vector<uint32_t> &host = host_tables();
+    auto *t = new XorwowSkipTables();
+    cudaError_t err = cudaMalloc(&t->d_tables, host.size() * sizeof(uint32_t));
+    if (err == cudaSuccess)
+        err = cudaMemcpy(t->d_tables, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        xorwow_tables_destroy(t);
+        return err;
+    }
+    *out = t;
+    return cudaSuccess;
+}
+
+void xorwow_tables_destroy(XorwowSkipTables *t)
+{
+    if (!t) return;
+    if (t->d_tables) cudaFree(t->d_tables);
+    delete t;
+}
+
+// One thread per path.  All lanes of a warp test the same bit index and read the same table row
+// (a broadcast load); only the XOR is predicated on the lane's own state bit.
+__global__ void __launch_bounds__(256)
+xorwow_init_kernel(const uint32_t *__restrict__ tables, unsigned long long seed, unsigned long long first_path,
+                   unsigned long long n_local, XorwowState xs)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_local) return;
+    // seed scramble of XORWOW as cuRAND defines it (curand_kernel.h:807-818)
+    const uint32_t s0 = (uint32_t)seed ^ 0xaad26b49u;
+    const uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    const uint32_t t0 = 1099087573u * s0;
+    const uint32_t t1 = 2591861531u * s1;
+    uint32_t v[5] = {123456789u + t0, 362436069u ^ t0, 521288629u + t1, 88675123u ^ t1, 5783321u + t0};
+    const uint32_t d = 6615241u + t1 + t0;
+
+    unsigned long long sub = first_path + idx;
+    for (int m = 0; sub != 0ull; ++m, sub >>= 2) {
+        const unsigned q = (unsigned)(sub & 3ull);
+        if (q == 0u) continue;
+        const uint4 *M = reinterpret_cast<const uint4 *>(tables + ((size_t)m * 3 + (q - 1)) * 160 * kRowWords);
+        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+#pragma unroll
+        for (int w = 0; w < 5; ++w) {
+            const uint32_t word = v[w];
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const uint4 a = __ldg(M + 2 * (w * 32 + j));
+                const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t *>(M + 2 * (w * 32 + j) + 1));
+                const uint32_t mask = 0u - ((word >> j) & 1u);
+                r0 ^= a.x & mask; r1 ^= a.y & mask; r2 ^= a.z & mask; r3 ^= a.w & mask; r4 ^= b4 & mask;
+            }
+        }
+        v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3; v[4] = r4;
+    }
+    xs.d[idx] = d;
+    xs.v0[idx] = v[0]; xs.v1[idx] = v[1]; xs.v2[idx] = v[2]; xs.v3[idx] = v[3]; xs.v4[idx] = v[4];
+    if (xs.bm_flag) {
+        xs.bm_flag[idx] = 0;
+        xs.bm_extra[idx] = 0.0f;
+        xs.bm_flag_d[idx] = 0;
+        xs.bm_extra_d[idx] = 0.0;
+    }
+}
+
+cudaError_t launch_xorwow_init(const XorwowSkipTables *t, unsigned long long seed, unsigned long long first_path,
+                               unsigned long long n_local, XorwowState xs, cudaStream_t stream)
+{
+    if (n_local == 0) return cudaSuccess;
+    const unsigned long long blocks = (n_local + 255ull) / 256ull;
+    xorwow_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(t->d_tables, seed, first_path, n_local, xs);
+    return cudaGetLastError();
+}
+
+}  // namespace nmchb

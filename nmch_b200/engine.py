@@ -1,0 +1,138 @@
+"""Thin object wrapper over the C ABI: one Engine == one nmch_engine_t handle.
+
+This is host plumbing only (argument packing, numpy views); all arithmetic happens in the CUDA
+library.  Mirrors the lifecycle of the reference's method objects (init / compute / finalize,
+/root/reference/include/NMCH/methods/NMCH.hpp:42-60).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import (FLOOR_ABS, FLOOR_PLUS, METHOD_EM, METHOD_FE, RNG_PHILOX, RNG_PHILOX_COMPAT,  # noqa: F401
+                   RNG_XORWOW_COMPAT)
+
+
+@dataclass
+class Moments:
+    """Raw FP64 sums of one compute() pass and the statistics the reference derives from them."""
+    sum_payoff: float
+    sum_payoff_sq: float
+    n_paths: int
+    exec_ms: float
+
+    @property
+    def mean(self) -> float:            # E[X]   (strike_price in the reference's naming)
+        return self.sum_payoff / self.n_paths
+
+    @property
+    def mean_sq(self) -> float:         # E[X^2] (price_squared)
+        return self.sum_payoff_sq / self.n_paths
+
+    @property
+    def variance(self) -> float:
+        return max(self.mean_sq - self.mean * self.mean, 0.0)
+
+    @property
+    def std_error(self) -> float:
+        return float(np.sqrt(self.variance / self.n_paths))
+
+    def merged(self, other: "Moments") -> "Moments":
+        return Moments(self.sum_payoff + other.sum_payoff, self.sum_payoff_sq + other.sum_payoff_sq,
+                       self.n_paths + other.n_paths, max(self.exec_ms, other.exec_ms))
+
+
+class Engine:
+    def __init__(self, NTPB=512, NB=512, T=1.0, S_0=1.0, v_0=0.1, r=0.0, k=0.5, rho=-0.7, theta=0.1, sigma=0.3,
+                 N=1000, method=METHOD_FE, floor=FLOOR_ABS, rng=RNG_PHILOX, device=-1, n_paths=0, first_path=0,
+                 n_local=0, paths_per_thread=0, block_threads=0):
+        self._lib = capi.load()
+        self.params = capi.NmchParams(NTPB, NB, T, S_0, v_0, r, k, rho, theta, sigma, N, method, floor, rng,
+                                      device, n_paths, first_path, n_local, paths_per_thread, block_threads)
+        self._h = C.c_void_p()
+        capi.check(self._lib.nmch_engine_create(C.byref(self.params), C.byref(self._h)))
+        self.n_paths = n_paths or NTPB * NB
+        self.n_local = n_local or (self.n_paths - first_path)
+        self.N = N
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def init(self, seed: int = 1234) -> "Engine":
+        capi.check(self._lib.nmch_engine_init(self._h, seed))
+        return self
+
+    def set_params(self, k: float, theta: float, sigma: float) -> None:
+        capi.check(self._lib.nmch_engine_set_params(self._h, k, theta, sigma))
+
+    def compute(self) -> Moments:
+        m = capi.NmchMoments()
+        capi.check(self._lib.nmch_engine_compute(self._h, C.byref(m)))
+        return Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms)
+
+    def compute_async(self, stream_ptr: int, d_moments_ptr: int) -> None:
+        """Enqueue one pass on a caller stream; raw sums land in device memory (2 doubles)."""
+        capi.check(self._lib.nmch_engine_compute_async(self._h, C.c_void_p(stream_ptr), C.c_void_p(d_moments_ptr)))
+
+    def explore(self, k, theta, sigma):
+        k = np.ascontiguousarray(k, np.float32)
+        theta = np.ascontiguousarray(theta, np.float32)
+        sigma = np.ascontiguousarray(sigma, np.float32)
+        n = len(k)
+        out = (capi.NmchMoments * n)()
+        f32p = C.POINTER(C.c_float)
+        capi.check(self._lib.nmch_engine_explore(self._h, k.ctypes.data_as(f32p), theta.ctypes.data_as(f32p),
+                                                 sigma.ctypes.data_as(f32p), n, out))
+        return [Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms) for m in out]
+
+    def explore_async(self, stream_ptr: int, k, theta, sigma, d_moments_ptr: int) -> None:
+        k = np.ascontiguousarray(k, np.float32)
+        theta = np.ascontiguousarray(theta, np.float32)
+        sigma = np.ascontiguousarray(sigma, np.float32)
+        f32p = C.POINTER(C.c_float)
+        capi.check(self._lib.nmch_engine_explore_async(self._h, C.c_void_p(stream_ptr), k.ctypes.data_as(f32p),
+                                                       theta.ctypes.data_as(f32p), sigma.ctypes.data_as(f32p),
+                                                       len(k), C.c_void_p(d_moments_ptr)))
+
+    def compute_paths(self, count: int | None = None):
+        """Parity hook: one compute() pass that also returns terminal S, V of local paths [0, count)."""
+        count = self.n_local if count is None else count
+        S = np.empty(count, np.float32)
+        V = np.empty(count, np.float32)
+        m = capi.NmchMoments()
+        f32p = C.POINTER(C.c_float)
+        capi.check(self._lib.nmch_engine_compute_paths(self._h, S.ctypes.data_as(f32p), V.ctypes.data_as(f32p),
+                                                       count, C.byref(m)))
+        return S, V, Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms)
+
+    def finalize(self) -> None:
+        if self._h:
+            capi.check(self._lib.nmch_engine_finalize(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.nmch_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    # -- reports -----------------------------------------------------------------------------
+    @property
+    def init_ms(self) -> float:
+        return self._lib.nmch_engine_init_ms(self._h)
+
+    def launch_info(self) -> dict:
+        li = capi.NmchLaunchInfo()
+        capi.check(self._lib.nmch_engine_launch_info(self._h, C.byref(li)))
+        return {n: getattr(li, n) for n, _ in li._fields_}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

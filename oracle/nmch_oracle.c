@@ -453,6 +453,51 @@ void orc_fe_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t se
     if (sumsq) *sumsq = acc2;
 }
 
+/* The exploration sweep (exploration.cu:71-88): one set_* + compute() per point on CONTINUED
+ * per-path streams; sums[2*i], sums[2*i+1] = raw payoff moments of point i. */
+void orc_fe_sweep(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,
+                  uint64_t first_path, uint64_t n_paths, int n_points, const float *k, const float *theta,
+                  const float *sigma, double *sums, int threads)
+{
+    const float dt = p->T / p->N;
+    const float K = p->S_0;
+    const float sqrt_dt = sqrtf(dt);
+    const float sqrt_rho = sqrtf(1 - p->rho * p->rho);
+    xorwow_build_matrices();
+    if (threads <= 0) threads = orc_max_threads();
+    for (int i = 0; i < 2 * n_points; ++i) sums[i] = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads)
+#endif
+    {
+        double *loc = (double *)calloc((size_t)2 * n_points, sizeof(double));
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+            orc_rng_t st;
+            orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, 0);
+            for (int pt = 0; pt < n_points; ++pt) {
+                float St = p->S_0, Vt = p->v_0;
+                for (int n = 0; n < p->N; ++n) {
+                    float gx, gy;
+                    orc_normal2(&st, &gx, &gy);
+                    fe_step(&St, &Vt, gx, gy, p->r, k[pt], p->rho, theta[pt], sigma[pt], dt, sqrt_dt, sqrt_rho,
+                            floor_kind);
+                }
+                float pay = fmaxf(0.0f, St - K);
+                loc[2 * pt] += (double)pay;
+                loc[2 * pt + 1] += (double)pay * (double)pay;
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical(orc_sweep)
+#endif
+        for (int i = 0; i < 2 * n_points; ++i) sums[i] += loc[i];
+        free(loc);
+    }
+}
+
 /* ======================================================================== */
 /* EM  (NMCH_EM.cu:213-260)                                                  */
 /* ======================================================================== */

@@ -73,6 +73,12 @@ void orc_fe_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t se
                 uint64_t first_path, uint64_t n_paths, int calls,
                 float *S_out, float *V_out, double *sum, double *sumsq, int threads);
 
+/* The exploration sweep (src/NMCH/test/exploration.cu:71-88): per point set_k/theta/sigma + compute()
+ * on continued streams.  sums has 2*n_points entries (raw sum, raw sum of squares per point). */
+void orc_fe_sweep(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,
+                  uint64_t first_path, uint64_t n_paths, int n_points, const float *k, const float *theta,
+                  const float *sigma, double *sums, int threads);
+
 /* --- EM (src/NMCH/methods/NMCH_EM.cu:11-55, 213-260) ---------------------- */
 void orc_em_run(const orc_params_t *p, int rng_kind, uint64_t seed,
                 uint64_t first_path, uint64_t n_paths, int calls,

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.orc_gamma.restype = C.c_float
         L.orc_fe_run.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                  C.c_int, f32p, f32p, f64p, f64p, C.c_int]
+        L.orc_fe_sweep.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
+                                   C.c_int, f32p, f32p, f32p, f64p, C.c_int]
         L.orc_em_run.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                  C.c_int, f32p, f32p, f64p, f64p, C.c_int]
         L.orc_em_exact_run.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint64, f64p, f64p, f64p, C.c_int]
@@ -165,6 +167,19 @@ def fe_run(p: Params, rng=RNG_XORWOW, floor=FLOOR_ABS, seed=1234, first_path=0, 
            want_paths=False, threads=0):
     """Reference FE kernel semantics (NMCH_FE.cu:145-175) for paths [first_path, first_path+n_paths)."""
     return _run(lib().orc_fe_run, p, (rng, floor, seed), first_path, n_paths, calls, want_paths, threads)
+
+
+def fe_sweep(p: Params, k, theta, sigma, rng=RNG_XORWOW, floor=FLOOR_ABS, seed=1234, first_path=0, n_paths=1024,
+             threads=0):
+    """exploration.cu:71-88 for FE: returns an (n_points, 2) array of raw payoff sums."""
+    k = np.ascontiguousarray(k, np.float32)
+    theta = np.ascontiguousarray(theta, np.float32)
+    sigma = np.ascontiguousarray(sigma, np.float32)
+    sums = np.zeros(2 * len(k), np.float64)
+    cp = p.c()
+    lib().orc_fe_sweep(C.byref(cp), rng, floor, seed, first_path, n_paths, len(k), _fp(k, C.c_float),
+                       _fp(theta, C.c_float), _fp(sigma, C.c_float), _fp(sums, C.c_double), threads)
+    return sums.reshape(-1, 2)
 
 
 def em_run(p: Params, rng=RNG_XORWOW, seed=1234, first_path=0, n_paths=1024, calls=1, want_paths=False,

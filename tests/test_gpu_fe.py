@@ -1,0 +1,257 @@
+"""GPU parity tests of the FE hot path, through the C ABI (ctypes -> libnmch_b200.so).
+
+Bars (BASELINE.json north_star):
+  * XORWOW-/Philox-compat modes vs the oracle: per-path within 2e-4 relative (host libm vs device
+    __sincosf/logf differ in the last bits), aggregates within 2e-5 absolute.
+  * compat modes vs the reference's own CUDA build (oracle/_ref/nmch_ref_harness, when shipped):
+    1e-5 relative on E[X] and on the variance.
+  * native Philox mode: within 3 standard errors of the oracle / reference and of the semi-analytic
+    Heston price (+ the O(dt) Euler scheme bias the oracle itself shows).
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+E = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _engine_module():
+    global E
+    from nmch_b200 import engine as _e
+    E = _e
+    yield
+
+
+def run_engine(n, N=1000, rng=None, floor=0, seed=1234, calls=1, paths=False, **kw):
+    ntpb = min(n, 512)
+    with E.Engine(NTPB=ntpb, NB=n // ntpb, N=N, rng=rng, floor=floor, **kw) as e:
+        e.init(seed)
+        for _ in range(calls - 1):
+            e.compute()
+        if paths:
+            return e.compute_paths()
+        return e.compute()
+
+
+# ---------------------------------------------------------------------------------------------
+# compat modes vs the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rng_e,rng_o", [(1, o.RNG_XORWOW), (2, o.RNG_PHILOX)])
+@pytest.mark.parametrize("floor", [0, 1])
+def test_compat_per_path_matches_oracle(rng_e, rng_o, floor):
+    n, N = 4096, 200
+    S, V, m = run_engine(n, N, rng=rng_e, floor=floor, paths=True)
+    ref = o.fe_run(o.Params(N=N), rng=rng_o, floor=floor, n_paths=n, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(V, ref["V"], rtol=5e-4, atol=2e-5)
+    assert abs(m.mean - ref["mean"]) < 2e-5 and abs(m.mean_sq - ref["mean_sq"]) < 2e-5
+    assert m.n_paths == n
+
+
+def test_compat_xorwow_golden_paths():
+    # SURVEY.md §8c per-path pins (seed 1234, README parameters, N = 1000)
+    S, V, _ = run_engine(512, 1000, rng=1, paths=True)
+    np.testing.assert_allclose(S[:3], [1.04778862, 1.15117562, 1.08905244], rtol=2e-4)
+    np.testing.assert_allclose(V[:3], [0.0700202361, 0.0975258127, 0.166186899], rtol=5e-4)
+
+
+def test_compat_xorwow_c1_aggregate():
+    m = run_engine(512 * 512, 1000, rng=1)
+    assert abs(m.mean - 0.120281939) < 2e-5
+    assert abs(m.mean_sq - 0.045731643) < 2e-5
+
+
+def test_compat_stream_continues_across_calls():
+    n, N = 2048, 64
+    S, V, m = run_engine(n, N, rng=1, calls=3, paths=True)
+    ref = o.fe_run(o.Params(N=N), rng=o.RNG_XORWOW, n_paths=n, calls=3, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=2e-4, atol=2e-5)
+    S, V, m = run_engine(n, 63, rng=2, calls=3, paths=True)          # odd N: Philox resumes mid-block
+    ref = o.fe_run(o.Params(N=63), rng=o.RNG_PHILOX, n_paths=n, calls=3, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=2e-4, atol=2e-5)
+
+
+def test_compat_shard_offsets_select_subsequences():
+    n, N = 8192, 50
+    full = o.fe_run(o.Params(N=N), rng=o.RNG_XORWOW, n_paths=n, want_paths=True)
+    with E.Engine(NTPB=512, NB=n // 512, N=N, rng=1, first_path=4096 + 17, n_local=1000) as e:
+        e.init(1234)
+        S, V, m = e.compute_paths()
+    np.testing.assert_allclose(S, full["S"][4113:5113], rtol=2e-4, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# compat modes vs the reference's CUDA build
+# ---------------------------------------------------------------------------------------------
+def _ref_cuda(**flags):
+    exe = o.REF_HARNESS_PATH
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/nmch_ref_harness not shipped")
+    cmd = [exe]
+    for k, v in flags.items():
+        cmd += [f"--{k}", str(v)]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600).stdout
+    return [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+
+
+def _rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+@pytest.mark.parametrize("rng_name,rng_e", [("xorwow", 1), ("philox", 2)])
+@pytest.mark.parametrize("cfg", [dict(NTPB=512, NB=512, N=1000), dict(NTPB=128, NB=64, N=333),
+                                 dict(NTPB=512, NB=512, N=1000, k=2.08, theta=0.108, sigma=1.0)])
+def test_compat_matches_reference_cuda_build(rng_name, rng_e, cfg):
+    ref = _ref_cuda(method="fe", rng=rng_name, kernel="k3", repeat=2, **cfg)
+    kw = {k: cfg[k] for k in ("k", "theta", "sigma") if k in cfg}
+    with E.Engine(NTPB=cfg["NTPB"], NB=cfg["NB"], N=cfg["N"], rng=rng_e, **kw) as e:
+        e.init(1234)
+        for call in range(2):
+            m = e.compute()
+            r = ref[call]
+            assert r["cuda"] == "cudaSuccess"
+            var_ref = r["E2"] - r["E"] ** 2
+            # tolerance of the north star: 1e-5 relative on price and variance (the reference's own
+            # float-atomic accumulation carries ~1e-6 of noise at this size)
+            assert _rel(m.mean, r["E"]) < 1e-5, (call, m.mean, r["E"])
+            assert _rel(m.variance, var_ref) < 1e-5, (call, m.variance, var_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# native Philox mode
+# ---------------------------------------------------------------------------------------------
+def test_native_per_path_tracks_oracle_philox():
+    # same Philox words per (path, step); fast-math transforms differ by ~2^-23 per draw
+    n, N = 4096, 100
+    S, V, m = run_engine(n, N, rng=0, paths=True)
+    ref = o.fe_run(o.Params(N=N), rng=o.RNG_PHILOX, n_paths=n, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(V, ref["V"], rtol=1e-2, atol=5e-4)
+
+
+@pytest.mark.parametrize("floor", [0, 1])
+def test_native_price_within_3se(floor):
+    n = 1 << 20
+    m = run_engine(n, 1000, rng=0, floor=floor)
+    ref = o.fe_run(o.Params(), rng=o.RNG_PHILOX, floor=floor, n_paths=1 << 16)
+    se_ref = o.std_error(ref["mean"], ref["mean_sq"], 1 << 16)
+    assert abs(m.mean - ref["mean"]) < 3 * np.hypot(m.std_error, se_ref)
+    assert abs(m.mean - o.heston_call()) < 3 * m.std_error + 2e-4        # + O(dt) Euler bias
+    assert abs(m.variance - (ref["mean_sq"] - ref["mean"] ** 2)) < 0.02 * m.variance
+
+
+def test_native_feller_violating_point_floors_differ():
+    n = 1 << 20
+    kw = dict(k=2.08, theta=0.108, sigma=1.0)
+    a = run_engine(n, 1000, rng=0, floor=0, **kw)
+    p = run_engine(n, 1000, rng=0, floor=1, **kw)
+    # abs 0.112979, plus 0.111989 (SE 3e-4 at 2^18)
+    assert abs(a.mean - 0.112979494) < 4 * 3.0e-4
+    assert abs(p.mean - 0.111988764) < 4 * 3.0e-4
+    assert a.mean > p.mean
+
+
+def test_native_paths_per_thread_and_block_size_do_not_change_paths():
+    n, N = 8192, 77
+    base = run_engine(n, N, rng=0, paths=True, paths_per_thread=1)
+    for P, bt in [(2, 256), (4, 256), (8, 256), (4, 128)]:
+        S, V, m = run_engine(n, N, rng=0, paths=True, paths_per_thread=P, block_threads=bt)
+        np.testing.assert_array_equal(S, base[0])
+        np.testing.assert_array_equal(V, base[1])
+        assert abs(m.sum_payoff - base[2].sum_payoff) < 1e-9 * n
+
+
+def test_native_deterministic_and_stream_continues():
+    a = run_engine(1 << 16, 100, rng=0)
+    b = run_engine(1 << 16, 100, rng=0)
+    assert a.sum_payoff == b.sum_payoff and a.sum_payoff_sq == b.sum_payoff_sq
+    c = run_engine(1 << 16, 100, rng=0, calls=2)
+    assert c.sum_payoff != a.sum_payoff
+    # second call of an odd-N run resumes mid-block and equals the oracle's continued stream
+    S, V, _ = run_engine(4096, 51, rng=0, calls=2, paths=True)
+    ref = o.fe_run(o.Params(N=51), rng=o.RNG_PHILOX, n_paths=4096, calls=2, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=2e-3, atol=2e-4)
+
+
+def test_native_sharding_is_additive():
+    n, N = 1 << 16, 100
+    whole = run_engine(n, N, rng=0)
+    parts = []
+    for g in range(4):
+        with E.Engine(NTPB=512, NB=n // 512, N=N, rng=0, first_path=g * n // 4, n_local=n // 4) as e:
+            e.init(1234)
+            parts.append(e.compute())
+    s = sum(p.sum_payoff for p in parts)
+    s2 = sum(p.sum_payoff_sq for p in parts)
+    assert abs(s - whole.sum_payoff) < 1e-9 * n and abs(s2 - whole.sum_payoff_sq) < 1e-9 * n
+
+
+def test_ragged_path_counts():
+    for n in (1, 31, 1000, 4097):
+        with E.Engine(NTPB=1, NB=n, N=20, rng=0, n_paths=n) as e:
+            e.init(5)
+            S, V, m = e.compute_paths()
+        ref = o.fe_run(o.Params(N=20), rng=o.RNG_PHILOX, seed=5, n_paths=n, want_paths=True)
+        np.testing.assert_allclose(S, ref["S"], rtol=2e-3, atol=2e-4)
+        assert m.n_paths == n
+        assert abs(m.sum_payoff - np.maximum(S.astype(np.float64) - 1.0, 0).sum()) < 1e-6 * max(n, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# exploration grid in one launch == sequential set_params + compute
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rng", [0, 1, 2])
+def test_explore_equals_sequential_computes(rng):
+    k, th, sg = o.exploration_grid(5, apply_filter=True)
+    k, th, sg = k[:12], th[:12], sg[:12]
+    n, N = 5120, 100                                        # the reference's sweep size (exploration.cu:24-25)
+    with E.Engine(NTPB=512, NB=10, N=N, rng=rng) as e:
+        e.init(1234)
+        batched = e.explore(k, th, sg)
+    with E.Engine(NTPB=512, NB=10, N=N, rng=rng) as e:
+        e.init(1234)
+        seq = []
+        for i in range(len(k)):
+            e.set_params(float(k[i]), float(th[i]), float(sg[i]))
+            seq.append(e.compute())
+    for b, s in zip(batched, seq):
+        assert b.sum_payoff == s.sum_payoff and b.sum_payoff_sq == s.sum_payoff_sq
+
+
+def test_explore_compat_matches_oracle_sweep():
+    k, th, sg = o.exploration_grid(5, apply_filter=True)
+    k, th, sg = k[:6], th[:6], sg[:6]
+    n, N = 1024, 50
+    with E.Engine(NTPB=512, NB=2, N=N, rng=1) as e:
+        e.init(1234)
+        got = e.explore(k, th, sg)
+    sums = o.fe_sweep(o.Params(N=N), k, th, sg, rng=o.RNG_XORWOW, n_paths=n)
+    for i, m in enumerate(got):
+        assert abs(m.sum_payoff - sums[i, 0]) < 2e-5 * n, i
+        assert abs(m.sum_payoff_sq - sums[i, 1]) < 2e-5 * n, i
+
+
+# ---------------------------------------------------------------------------------------------
+# lifecycle / error behaviour
+# ---------------------------------------------------------------------------------------------
+def test_lifecycle_errors():
+    from nmch_b200 import capi
+    e = E.Engine(NTPB=32, NB=4, N=10)
+    with pytest.raises(capi.NmchError) as ei:
+        e.compute()
+    assert ei.value.status == capi.ERR_STATE
+    e.init(1)
+    e.compute()
+    e.finalize()
+    e.finalize()                                            # idempotent (the reference double-frees)
+    with pytest.raises(capi.NmchError):
+        e.compute()
+    e.close()
