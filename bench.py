@@ -225,7 +225,8 @@ def main():
                    paths_per_thread=args.paths_per_thread, block_threads=args.block_threads, **README)
     eng.init(1234)
     moments = torch.zeros(2, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)             # one stream carries the kernel and the allreduce
+    torch.cuda.set_stream(stream)
 
     def step():
         eng.compute_async(stream.cuda_stream, moments.data_ptr())

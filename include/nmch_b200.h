@@ -74,7 +74,7 @@ int nmch_engine_init(nmch_engine_t *e, unsigned long long seed);
 int nmch_engine_set_params(nmch_engine_t *e, float k, float theta, float sigma);
 /* compute() (NMCH_FE.cu:516-546): one pass over all local paths, streams continue across calls */
 int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out);
-/* Same pass, asynchronous: enqueued on `cuda_stream` (a cudaStream_t; NULL = the engine's stream),
+/* Same pass, asynchronous: enqueued on `cuda_stream` (a cudaStream_t; NULL = the CUDA default stream),
  * raw sums {sum, sumsq} written to the DEVICE buffer d_moments[2] (e.g. an NCCL send buffer), no host
  * sync, no exec_ms.  This is what the multi-GPU layer calls before its single allreduce. */
 int nmch_engine_compute_async(nmch_engine_t *e, void *cuda_stream, double *d_moments);

@@ -1,15 +1,480 @@
-// em_kernels.cu -- EM ("exact method") kernels.  Placeholder until the EM path lands: every entry point
-// reports the missing feature loudly (no CPU fallback).
+// em_kernels.cu -- "exact method" (EM) Heston path kernels for sm_100a.
+//
+// Reference scheme (src/NMCH/methods/NMCH_EM.cu:213-260): per time step the variance makes an EXACT CIR
+// transition  V' = c * Gamma(d + Poisson(lc * V)),  c = sigma^2 (1-e^{-k dt}) / (2k),  d = 2 k theta / sigma^2,
+// lc = 2k e^{-k dt} / (sigma^2 (1 - e^{-k dt}));  the integrated variance is the trapezoid sum; one conditional
+// log-normal draw gives S_T.
+//
+// em_native_kernel -- the product path.  V'/c is a scaled noncentral chi-square, sampled exactly by
+//   d > 1/2 :  Gamma(d + Poisson(l)) =d= (Z + sqrt(2 l))^2 / 2 + Gamma(d - 1/2)           (one normal, one gamma
+//              of CONSTANT shape: Marsaglia-Tsang constants are per-point, no Poisson, no data-dependent regime)
+//   d <= 1/2:  Poisson (inversion below 10, Hoermann PTRS above) then Marsaglia-Tsang gamma of shape d + N
+//   Rejections do not loop inside a step: every loop iteration is ONE trial on a fresh Philox block and a lane
+//   commits its step only if the trial accepted, so a warp never waits on its slowest lane's retry.
+// em_compat_kernel -- validation path: the reference's own draw sequence (cuRAND's curand_poisson /
+//   curand_normal / curand_uniform on a cuRAND-layout state) and its FP32 expressions, so results can be
+//   compared with the reference's CUDA build on identical seeds.
+#include <curand_kernel.h>
+
+#include <vector>
+
 #include "engine_internal.cuh"
 
 namespace nmchb {
 
-int em_launch_points(nmch_engine *, cudaStream_t, const float *, const float *, const float *, int, double *,
-                     float *, float *)
+// ------------------------------------------------------------------------------------------
+// native kernel
+// ------------------------------------------------------------------------------------------
+struct EmPoint {
+    float scale;        // c
+    float two_lc;       // 2 * lc
+    float lc;
+    float d;            // 2 k theta / sigma^2
+    float a;            // fast path: gamma shape d - 1/2 (boosted by +1 when < 1)
+    float mt_d, mt_c;   // Marsaglia-Tsang constants of the fast path's gamma
+    float inv_a;        // 1/a when boosting, else 0
+    float k, ktheta_T, inv_sigma;
+    int   fast;         // 1: d - 1/2 > 0, chi-square split; 0: Poisson-mixture path
+};
+
+struct EmLaunch {
+    PhiloxKeys keys;
+    unsigned long long first_path, n_local;
+    unsigned int call0;              // stream id of point 0 (engine call counter)
+    int   N, n_points, blocks_per_point;
+    float v0, K, half_dt, rho, one_m_rho2, lnS0_rT;
+    EmPoint pt0;
+};
+
+__device__ __forceinline__ float u01_open(uint32_t w)          // (0,1), 23 bits
 {
-    return engine_fail(NMCH_ERR_ARG, "EM method not built yet");
+    return bits_to_1_2(w) - 0.99999994f;
 }
-int em_philox_compat_init(nmch_engine *) { return NMCH_OK; }
-void em_release(nmch_engine *) {}
+
+__device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, float &n1, float &n2)
+{
+    const float r = sqrt_approx(-1.38629436f * lg2_approx(u01_open(wa)));     // sqrt(-2 ln u)
+    const float ang = bits_to_1_2(wb) * 6.2831855f;
+    n1 = r * sin_approx(ang);
+    n2 = r * cos_approx(ang);
+}
+
+// One Marsaglia-Tsang trial for Gamma(shape >= 1) given x ~ N(0,1), u ~ U(0,1).  Returns accept; g = d*v^3.
+__device__ __forceinline__ bool mt_trial(float x, float u, float mt_d, float mt_c, float &g)
+{
+    const float v1 = fmaf(mt_c, x, 1.0f);
+    const float v = v1 * v1 * v1;
+    const float x2 = x * x;
+    g = mt_d * v;
+    if (v1 <= 0.0f) return false;
+    if (u < fmaf(-0.0331f * x2, x2, 1.0f)) return true;                          // squeeze
+    return __logf(u) < fmaf(0.5f, x2, mt_d * (1.0f - v + __logf(v)));
+}
+
+__constant__ float kLnFactorial[10] = {0.0f, 0.0f, 0.69314718f, 1.79175947f, 3.17805383f, 4.78749174f,
+                                       6.57925121f, 8.52516136f, 10.6046029f, 12.8018275f};
+__device__ __forceinline__ float ln_factorial_small(int k) { return kLnFactorial[k]; }
+
+// log of the Poisson pmf, FP32-stable for large mu (the textbook  -mu + k ln mu - lgamma(k+1)  cancels badly)
+__device__ __forceinline__ float poisson_log_pmf(float k, float mu)
+{
+    if (k < 10.0f) return -mu + k * logf(mu) - ln_factorial_small((int)k);
+    const float r = mu / k;
+    const float ik = 1.0f / k;
+    const float stirling = fmaf(ik * ik * ik, 1.0f / 360.0f, -ik * (1.0f / 12.0f));
+    return k * (logf(r) + (1.0f - r)) - 0.5f * logf(6.28318531f * k) + stirling;
+}
+
+// One Hoermann-PTRS trial (mu >= 10).  Returns accept, result in k.
+__device__ __forceinline__ bool ptrs_trial(float mu, float u_raw, float v, float &k)
+{
+    const float smu = sqrt_approx(mu);
+    const float b = fmaf(2.53f, smu, 0.931f);
+    const float a = fmaf(0.02483f, b, -0.059f);
+    const float inv_alpha = 1.1239f + 1.1328f / (b - 3.4f);
+    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    const float u = u_raw - 0.5f;
+    const float us = 0.5f - fabsf(u);
+    k = floorf(fmaf(2.0f * a / us + b, u, mu + 0.43f));
+    if (us >= 0.07f && v <= vr) return true;
+    if (k < 0.0f || (us < 0.013f && v > us)) return false;
+    return logf(v * inv_alpha / (a / (us * us) + b)) <= poisson_log_pmf(k, mu);
+}
+
+// Poisson by inversion (mu < 10): exact, one uniform.
+__device__ __forceinline__ float poisson_inversion(float mu, float u)
+{
+    float p = __expf(-mu), cdf = p, k = 0.0f;
+    while (u > cdf && k < 80.0f) {
+        k += 1.0f;
+        p *= mu / k;
+        cdf += p;
+    }
+    return k;
+}
+
+template <bool MIXED>
+__global__ void __launch_bounds__(256)
+em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__ pts, ReduceBuffers rb,
+                 float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    const int point = blockIdx.y;
+    const EmPoint pc = (pts != nullptr) ? pts[point] : L.pt0;
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < L.n_local;
+    const unsigned long long g = L.first_path + idx;
+    const uint32_t path_lo = (uint32_t)g, path_hi = (uint32_t)(g >> 32);
+    const uint32_t stream = L.call0 + (uint32_t)point;      // ctr.y: one stream per compute() call / point
+
+    float V = L.v0, vI = 0.0f, S = 0.0f;
+    if (valid) {
+        uint32_t blk = 0;
+        int step = 0;
+        bool have_np = false;
+        float np = 0.0f;
+        while (step < L.N) {
+            const U4 w = philox4x32_10(blk++, stream, path_lo, path_hi, L.keys);
+            float gsum;
+            bool accept;
+            if (!MIXED || pc.fast) {
+                float z, x, gam;
+                box_muller_fast(w.x, w.y, z, x);
+                accept = mt_trial(x, u01_open(w.z), pc.mt_d, pc.mt_c, gam);
+                if (pc.inv_a != 0.0f) gam *= ex2_approx(pc.inv_a * lg2_approx(u01_open(w.w)));   // shape < 1 boost
+                const float t = z + sqrt_approx(pc.two_lc * V);
+                gsum = fmaf(0.5f * t, t, gam);
+            } else {
+                if (!have_np) {
+                    const float mu = pc.lc * V;
+                    if (mu < 10.0f) {
+                        np = poisson_inversion(mu, u01_open(w.x));
+                        have_np = true;
+                    } else {
+                        have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), np);
+                    }
+                }
+                accept = false;
+                gsum = 0.0f;
+                if (have_np) {
+                    const U4 w2 = philox4x32_10(blk++, stream, path_lo, path_hi, L.keys);
+                    float x, unused;
+                    box_muller_fast(w2.x, w2.y, x, unused);
+                    float shape = pc.d + np, boost = 1.0f;
+                    if (shape < 1.0f) {
+                        boost = ex2_approx(lg2_approx(u01_open(w2.w)) / shape);
+                        shape += 1.0f;
+                    }
+                    const float md = shape - (1.0f / 3.0f);
+                    const float mc = rsqrt_approx(9.0f * md);
+                    float gam;
+                    accept = mt_trial(x, u01_open(w2.z), md, mc, gam);
+                    gsum = gam * boost;
+                }
+            }
+            if (accept) {
+                const float Vn = __fmul_rn(pc.scale, gsum);    // explicit roundings: both instantiations agree bit for bit
+                vI = __fadd_rn(vI, __fadd_rn(V, Vn));          // trapezoid sum, NMCH_EM.cu:243
+                V = Vn;
+                ++step;
+                have_np = false;
+            }
+        }
+        // terminal draw (NMCH_EM.cu:247-260, generalised to S_0, r, T)
+        const U4 w = philox4x32_10(blk, stream, path_lo, path_hi, L.keys);
+        float z, unused;
+        box_muller_fast(w.x, w.y, z, unused);
+        vI *= L.half_dt;
+        float m = pc.inv_sigma * (V - L.v0 - pc.ktheta_T + pc.k * vI);
+        m = fmaf(L.rho, m, fmaf(-0.5f, vI, L.lnS0_rT));
+        S = __expf(fmaf(sqrt_approx(L.one_m_rho2 * vI), z, m));
+    }
+    double pay = 0.0;
+    if (valid) {
+        pay = (double)fmaxf(0.0f, S - L.K);
+        if (S_out != nullptr && point == L.n_points - 1) {
+            S_out[idx] = S;
+            V_out[idx] = V;
+        }
+    }
+    block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+}
+
+// ------------------------------------------------------------------------------------------
+// compat kernel: the reference's draws (cuRAND device API on a cuRAND-layout state) and expressions
+// ------------------------------------------------------------------------------------------
+struct EmCompatLaunch {
+    unsigned long long n_local;
+    int   N, n_points, blocks_per_point;
+    float S0, v0, K, rho, dt;
+    RawPoint raw0;
+};
+
+// Marsaglia-Tsang exactly as the reference draws it (NMCH_EM.cu:11-55): boost uniform BEFORE the loop, one
+// cached-pair normal and one uniform per trial.
+template <typename State>
+__device__ __forceinline__ float gamma_compat(State *st, float alpha)
+{
+    float boost = 1.0f;
+    if (alpha < 1.0f) {
+        boost = powf(curand_uniform(st), 1.0f / alpha);
+        alpha += 1.0f;
+    }
+    const float d = alpha - 1.0f / 3.0f;
+    const float c = 1.0f / sqrtf(9.0f * d);
+    for (;;) {
+        float x, v;
+        do {
+            x = curand_normal(st);
+            v = 1.0f + c * x;
+        } while (v <= 0.0f);
+        v = v * v * v;
+        const float u = curand_uniform(st);
+        const float x2 = x * x;
+        if (u < 1.0f - 0.0331f * x2 * x2 || logf(u) < 0.5f * x2 + d * (1.0f - v + logf(v))) return d * v * boost;
+    }
+}
+
+template <typename State>
+__device__ __forceinline__ float em_path_compat(State *st, const EmCompatLaunch &L, const RawPoint &rp, float &V_T)
+{
+    const float k = rp.k, theta = rp.theta, sigma = rp.sigma, rho = L.rho, dt = L.dt, v_0 = L.v0;
+    const float exp_kdt = expf(-k * dt);
+    const float d = 2.0f * k * theta / (sigma * sigma);
+    const float lambda_const = (2 * k * exp_kdt) / (sigma * sigma * (1 - exp_kdt));
+    float Vt = v_0, vI = 0.0f;
+    for (int i = 0; i < L.N; ++i) {
+        const float lambda = lambda_const * Vt;
+        const int N_p = curand_poisson(st, lambda);
+        const float gam = gamma_compat(st, d + N_p);
+        const float Vt_next = (sigma * sigma * (1.0f - exp_kdt) / (2.0f * k)) * gam;
+        vI += (Vt + Vt_next);
+        Vt = Vt_next;
+    }
+    vI *= dt * 0.5;                                            // double multiply, NMCH_EM.cu:247
+    float m = (1.0f / sigma) * (Vt - v_0 - k * theta + k * vI);
+    m = -0.5f * vI + rho * m;
+    const float sigma2 = (1.0f - rho * rho) * vI;
+    V_T = Vt;
+    return expf(m + sqrtf(sigma2) * curand_normal(st));
+}
+
+__global__ void __launch_bounds__(256)
+em_compat_xorwow_kernel(const __grid_constant__ EmCompatLaunch L, const RawPoint *__restrict__ pts, XorwowState xs,
+                        ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < L.n_local;
+    curandStateXORWOW_t st;
+    if (valid) {
+        st.d = xs.d[idx];
+        st.v[0] = xs.v0[idx]; st.v[1] = xs.v1[idx]; st.v[2] = xs.v2[idx]; st.v[3] = xs.v3[idx]; st.v[4] = xs.v4[idx];
+        st.boxmuller_flag = xs.bm_flag[idx];
+        st.boxmuller_extra = xs.bm_extra[idx];
+        st.boxmuller_flag_double = xs.bm_flag_d[idx];
+        st.boxmuller_extra_double = xs.bm_extra_d[idx];
+    }
+    for (int point = 0; point < L.n_points; ++point) {
+        const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
+        double pay = 0.0;
+        if (valid) {
+            float V_T;
+            const float S = em_path_compat(&st, L, rp, V_T);
+            pay = (double)fmaxf(0.0f, S - L.K);
+            if (S_out != nullptr && point == L.n_points - 1) {
+                S_out[idx] = S;
+                V_out[idx] = V_T;
+            }
+        }
+        block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+    }
+    if (valid) {                                               // streams continue (NMCH_EM.cu:280)
+        xs.d[idx] = st.d;
+        xs.v0[idx] = st.v[0]; xs.v1[idx] = st.v[1]; xs.v2[idx] = st.v[2]; xs.v3[idx] = st.v[3]; xs.v4[idx] = st.v[4];
+        xs.bm_flag[idx] = st.boxmuller_flag;
+        xs.bm_extra[idx] = st.boxmuller_extra;
+        xs.bm_flag_d[idx] = st.boxmuller_flag_double;
+        xs.bm_extra_d[idx] = st.boxmuller_extra_double;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+em_compat_philox_kernel(const __grid_constant__ EmCompatLaunch L, const RawPoint *__restrict__ pts,
+                        curandStatePhilox4_32_10_t *__restrict__ states, ReduceBuffers rb,
+                        float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < L.n_local;
+    curandStatePhilox4_32_10_t st;
+    if (valid) st = states[idx];
+    for (int point = 0; point < L.n_points; ++point) {
+        const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
+        double pay = 0.0;
+        if (valid) {
+            float V_T;
+            const float S = em_path_compat(&st, L, rp, V_T);
+            pay = (double)fmaxf(0.0f, S - L.K);
+            if (S_out != nullptr && point == L.n_points - 1) {
+                S_out[idx] = S;
+                V_out[idx] = V_T;
+            }
+        }
+        block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+    }
+    if (valid) states[idx] = st;
+}
+
+// cuRAND Philox state for the compat path: counter = (0, 0, path, 0), key = seed (curand_kernel.h:1022-1037)
+__global__ void em_philox_state_init_kernel(curandStatePhilox4_32_10_t *states, unsigned long long seed,
+                                            unsigned long long first_path, unsigned long long n_local)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_local) curand_init(seed, first_path + idx, 0, &states[idx]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, float sigmaf)
+{
+    const double k = kf, theta = thetaf, sigma = sigmaf, dt = (double)p.T / p.N;
+    const double e = std::exp(-k * dt), om = -std::expm1(-k * dt);
+    EmPoint pt{};
+    pt.scale = (float)(sigma * sigma * om / (2.0 * k));
+    pt.lc = (float)(2.0 * k * e / (sigma * sigma * om));
+    pt.two_lc = 2.0f * pt.lc;
+    pt.d = (float)(2.0 * k * theta / (sigma * sigma));
+    double a = 2.0 * k * theta / (sigma * sigma) - 0.5;
+    pt.a = (float)a;
+    pt.inv_a = 0.0f;
+    if (a > 0.0) {
+        if (a < 1.0) {
+            pt.inv_a = (float)(1.0 / a);
+            a += 1.0;
+        }
+        const double md = a - 1.0 / 3.0;
+        pt.mt_d = (float)md;
+        pt.mt_c = (float)(1.0 / std::sqrt(9.0 * md));
+    }
+    pt.k = kf;
+    pt.ktheta_T = (float)(k * theta * (double)p.T);
+    pt.inv_sigma = (float)(1.0 / sigma);
+    pt.fast = (pt.a > 1e-3f) ? 1 : 0;      // tiny or negative d - 1/2 goes through the Poisson mixture
+    return pt;
+}
+
+
+int em_philox_compat_init(nmch_engine *e)
+{
+    const size_t n = (size_t)e->n_local;
+    cudaError_t err = cudaMalloc(&e->em_philox_states, n * sizeof(curandStatePhilox4_32_10_t));
+    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "cudaMalloc(philox states)", err);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    em_philox_state_init_kernel<<<blocks, 256, 0, e->stream>>>(
+        static_cast<curandStatePhilox4_32_10_t *>(e->em_philox_states), e->seed, e->first_path, e->n_local);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_philox_state_init_kernel", err);
+    e->launches += 1;
+    return NMCH_OK;
+}
+
+void em_release(nmch_engine *e)
+{
+    if (e->em_philox_states) cudaFree(e->em_philox_states);
+    e->em_philox_states = nullptr;
+}
+
+int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
+                     int n_points, double *d_out, float *S_out, float *V_out)
+{
+    const nmch_params_t &p = e->p;
+    const bool own = (k == nullptr);
+    const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
+    if (bpp == 0 || bpp > 0x7fffffffull) return engine_fail(NMCH_ERR_ARG, "launch grid out of range");
+    cudaError_t err;
+    if (p.rng == NMCH_RNG_PHILOX) {
+        std::vector<EmPoint> pts(n_points);
+        bool all_fast = true;
+        for (int i = 0; i < n_points; ++i) {
+            pts[i] = own ? fold_em_point(p, p.k, p.theta, p.sigma) : fold_em_point(p, k[i], theta[i], sigma[i]);
+            all_fast = all_fast && pts[i].fast;
+        }
+        int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(EmPoint));
+        if (rc) return rc;
+        const EmPoint *d_pts = nullptr;
+        if (!own) {
+            err = cudaMemcpyAsync(e->d_points, pts.data(), pts.size() * sizeof(EmPoint), cudaMemcpyHostToDevice, stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+            if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "EM point upload", err);
+            d_pts = static_cast<const EmPoint *>(e->d_points);
+        }
+        EmLaunch L{};
+        L.keys = philox_expand_keys(e->seed);
+        L.first_path = e->first_path;
+        L.n_local = e->n_local;
+        L.call0 = (unsigned int)e->em_calls;
+        L.N = p.N;
+        L.n_points = n_points;
+        L.blocks_per_point = (int)bpp;
+        L.v0 = p.v_0;
+        L.K = p.S_0;
+        L.half_dt = 0.5f * (p.T / (float)p.N);
+        L.rho = p.rho;
+        L.one_m_rho2 = 1.0f - p.rho * p.rho;
+        L.lnS0_rT = (float)(std::log((double)p.S_0) + (double)p.r * (double)p.T);
+        L.pt0 = pts[0];
+        ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
+        dim3 grid((unsigned)bpp, (unsigned)n_points, 1);
+        cudaFuncAttributes attr{};
+        if (all_fast) {
+            em_native_kernel<false><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            cudaFuncGetAttributes(&attr, em_native_kernel<false>);
+        } else {
+            em_native_kernel<true><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            cudaFuncGetAttributes(&attr, em_native_kernel<true>);
+        }
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_native_kernel", err);
+        e->kinfo = KernelInfo{(int)grid.x, (int)grid.y, 256, 1, attr.numRegs};
+        e->em_calls += (unsigned long long)n_points;
+        return NMCH_OK;
+    }
+    // compat modes
+    int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(RawPoint));
+    if (rc) return rc;
+    const RawPoint *d_pts = nullptr;
+    if (!own) {
+        std::vector<RawPoint> pts(n_points);
+        for (int i = 0; i < n_points; ++i) pts[i] = RawPoint{k[i], theta[i], sigma[i], 0.0f};
+        err = cudaMemcpyAsync(e->d_points, pts.data(), pts.size() * sizeof(RawPoint), cudaMemcpyHostToDevice, stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+        if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "EM point upload", err);
+        d_pts = static_cast<const RawPoint *>(e->d_points);
+    }
+    EmCompatLaunch L{};
+    L.n_local = e->n_local;
+    L.N = p.N;
+    L.n_points = n_points;
+    L.blocks_per_point = (int)bpp;
+    L.S0 = p.S_0;
+    L.v0 = p.v_0;
+    L.K = p.S_0;
+    L.rho = p.rho;
+    L.dt = p.T / (float)p.N;
+    L.raw0 = RawPoint{p.k, p.theta, p.sigma, 0.0f};
+    ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
+    cudaFuncAttributes attr{};
+    if (p.rng == NMCH_RNG_XORWOW_COMPAT) {
+        em_compat_xorwow_kernel<<<(unsigned)bpp, 256, 0, stream>>>(L, d_pts, e->xs, rb, S_out, V_out);
+        cudaFuncGetAttributes(&attr, em_compat_xorwow_kernel);
+    } else {
+        em_compat_philox_kernel<<<(unsigned)bpp, 256, 0, stream>>>(
+            L, d_pts, static_cast<curandStatePhilox4_32_10_t *>(e->em_philox_states), rb, S_out, V_out);
+        cudaFuncGetAttributes(&attr, em_compat_philox_kernel);
+    }
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_compat_kernel", err);
+    e->kinfo = KernelInfo{(int)bpp, 1, 256, 1, attr.numRegs};
+    return NMCH_OK;
+}
 
 }  // namespace nmchb

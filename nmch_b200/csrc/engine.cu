@@ -374,7 +374,7 @@ int nmch_engine_compute_async(nmch_engine_t *e, void *cuda_stream, double *d_mom
     if (!d_moments) return fail(NMCH_ERR_ARG, "null device output");
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
-    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);     // NULL = the CUDA default stream, as in the runtime API
     return launch_points(e, s, nullptr, nullptr, nullptr, 1, d_moments, nullptr, nullptr);
 }
 
@@ -409,7 +409,7 @@ int nmch_engine_explore_async(nmch_engine_t *e, void *cuda_stream, const float *
     if (n_points > 65535) return fail(NMCH_ERR_ARG, "at most 65535 points per launch");
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
-    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);     // NULL = the CUDA default stream, as in the runtime API
     return launch_points(e, s, k, theta, sigma, n_points, d_moments, nullptr, nullptr);
 }
 

@@ -32,6 +32,7 @@ struct nmch_engine {
     // XORWOW-compat state
     nmchb::XorwowSkipTables *xtab = nullptr;
     nmchb::XorwowState xs{};
+    void *em_philox_states = nullptr;        // curandStatePhilox4_32_10_t[n_local], EM Philox-compat only
     nmchb::KernelInfo kinfo{};
     unsigned long long launches = 0;
 };

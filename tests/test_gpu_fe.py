@@ -141,11 +141,23 @@ def test_native_per_path_tracks_oracle_philox():
 def test_native_price_within_3se(floor):
     n = 1 << 20
     m = run_engine(n, 1000, rng=0, floor=floor)
-    ref = o.fe_run(o.Params(), rng=o.RNG_PHILOX, floor=floor, n_paths=1 << 16)
-    se_ref = o.std_error(ref["mean"], ref["mean_sq"], 1 << 16)
-    assert abs(m.mean - ref["mean"]) < 3 * np.hypot(m.std_error, se_ref)
-    assert abs(m.mean - o.heston_call()) < 3 * m.std_error + 2e-4        # + O(dt) Euler bias
-    assert abs(m.variance - (ref["mean_sq"] - ref["mean"] ** 2)) < 0.02 * m.variance
+    # vs the semi-analytic Heston price (Euler bias at the README point is below 1e-4, cf. the reference's
+    # own 2^24-path XORWOW run: 0.119728 vs 0.119733)
+    assert abs(m.mean - o.heston_call()) < 3 * m.std_error + 1e-4
+    # vs the reference's arithmetic on the SAME Philox words (compat mode == reference CUDA build to 1e-5):
+    # the two estimates are almost perfectly correlated, so they must agree far inside one standard error
+    c = run_engine(n, 1000, rng=2, floor=floor)
+    assert abs(m.mean - c.mean) < 0.25 * m.std_error, (m.mean, c.mean, m.std_error)
+    assert abs(m.variance - c.variance) < 5e-3 * c.variance
+
+
+def test_native_vs_oracle_same_paths_full_length():
+    n = 1 << 13
+    S, V, m = run_engine(n, 1000, rng=0, paths=True)
+    ref = o.fe_run(o.Params(), rng=o.RNG_PHILOX, n_paths=n, want_paths=True)
+    # 1000 steps of ~2^-22 relative transform error per draw: per-path agreement to a few 1e-3
+    np.testing.assert_allclose(S, ref["S"], rtol=1e-2, atol=1e-3)
+    assert abs(m.mean - ref["mean"]) < 0.25 * m.std_error
 
 
 def test_native_feller_violating_point_floors_differ():
