@@ -219,19 +219,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = E.Engine(NTPB=512, NB=(n_per_gpu * world) // 512, N=N, method=E.METHOD_FE if args.method == "fe" else E.METHOD_EM,
-                   floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, rng=E.RNG_PHILOX, device=local_rank,
-                   n_paths=n_per_gpu * world, first_path=rank * n_per_gpu, n_local=n_per_gpu,
-                   paths_per_thread=args.paths_per_thread, block_threads=args.block_threads, **README)
-    eng.init(1234)
-    moments = torch.zeros(2, dtype=torch.float64, device=dev)
+    from nmch_b200.distributed import ShardedEngine
     stream = torch.cuda.Stream(dev)             # one stream carries the kernel and the allreduce
     torch.cuda.set_stream(stream)
+    sh = ShardedEngine(rank=rank, world=world, device=local_rank, NTPB=512, NB=(n_per_gpu * world) // 512, N=N,
+                       method=E.METHOD_FE if args.method == "fe" else E.METHOD_EM,
+                       floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, rng=E.RNG_PHILOX,
+                       paths_per_thread=args.paths_per_thread, block_threads=args.block_threads, **README)
+    sh.init(1234)
+    eng = sh.engine
+    assert eng.n_local == n_per_gpu
+    moments = None
 
     def step():
-        eng.compute_async(stream.cuda_stream, moments.data_ptr())
-        if world > 1:
-            dist.all_reduce(moments)             # the path's one exchange: 16 bytes of FP64 partial moments
+        nonlocal moments
+        moments = sh.compute_async()             # kernel -> (N>1: one NCCL allreduce of 16 bytes of FP64 moments)
 
     def barrier():
         if world > 1:

@@ -101,6 +101,23 @@ typedef struct {
 } nmch_launch_info_t;
 int nmch_engine_launch_info(const nmch_engine_t *e, nmch_launch_info_t *out);
 
+/* ---- multi-GPU group (one process, G devices): the path axis is sharded, paths [g*n/G, (g+1)*n/G) on
+ * device g with disjoint generator subsequences (global path index = subsequence, random.cu:8-9), and ONE
+ * ncclAllReduce(ncclDouble, ncclSum) over NVLink of the 2*n_points partial moments per compute()/explore().
+ * The reference has no multi-GPU path ("Distributed backend: none"); a group of 1 is a plain
+ * engine and needs no NCCL.  The C++ method classes (include/NMCH/methods/*.hpp) sit on this API. */
+typedef struct nmch_group nmch_group_t;
+int nmch_group_create(const nmch_params_t *params, int n_gpus, nmch_group_t **out);
+int nmch_group_init(nmch_group_t *g, unsigned long long seed);
+int nmch_group_set_params(nmch_group_t *g, float k, float theta, float sigma);
+int nmch_group_compute(nmch_group_t *g, nmch_moments_t *out);            /* out: GLOBAL sums, n_paths = n */
+int nmch_group_explore(nmch_group_t *g, const float *k, const float *theta, const float *sigma, int n_points,
+                       nmch_moments_t *out);
+int nmch_group_finalize(nmch_group_t *g);
+void nmch_group_destroy(nmch_group_t *g);
+float nmch_group_init_ms(const nmch_group_t *g);
+int nmch_group_size(const nmch_group_t *g);
+
 const char *nmch_status_string(int status);
 const char *nmch_last_error(void);          /* thread-local detail of the last failure */
 int nmch_device_count(void);

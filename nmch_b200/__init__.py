@@ -6,6 +6,6 @@ distributed.py (path sharding + one NCCL allreduce of the moments).
 There is no CPU fallback: importing is cheap, computing needs the CUDA library and a GPU.
 """
 from . import capi, engine, methods  # noqa: F401
-from .engine import Engine, Moments  # noqa: F401
+from .engine import Engine, Group, Moments  # noqa: F401
 
-__all__ = ["capi", "engine", "methods", "Engine", "Moments"]
+__all__ = ["capi", "engine", "methods", "Engine", "Group", "Moments"]

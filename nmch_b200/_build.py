@@ -18,7 +18,7 @@ BIN = os.path.join(ROOT, "bin")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
-CU_SOURCES = ["engine.cu", "fe_kernels.cu", "em_kernels.cu", "xorwow.cu"]
+CU_SOURCES = ["engine.cu", "fe_kernels.cu", "em_kernels.cu", "xorwow.cu", "group.cu"]
 
 
 def _newer(target: str, deps) -> bool:
@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(" ".join(cmd))
                 subprocess.run(cmd, check=True)
             objs.append(obj)
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

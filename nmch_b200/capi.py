@@ -39,7 +39,9 @@ EXPORTS = [
     "nmch_engine_create", "nmch_engine_init", "nmch_engine_set_params", "nmch_engine_compute",
     "nmch_engine_compute_async", "nmch_engine_explore", "nmch_engine_explore_async",
     "nmch_engine_compute_paths", "nmch_engine_finalize", "nmch_engine_destroy", "nmch_engine_init_ms",
-    "nmch_engine_launch_info", "nmch_status_string", "nmch_last_error", "nmch_device_count", "nmch_version",
+    "nmch_engine_launch_info", "nmch_group_create", "nmch_group_init", "nmch_group_set_params", "nmch_group_compute",
+    "nmch_group_explore", "nmch_group_finalize", "nmch_group_destroy", "nmch_group_init_ms", "nmch_group_size",
+    "nmch_status_string", "nmch_last_error", "nmch_device_count", "nmch_version",
 ]
 
 _lib = None
@@ -74,6 +76,17 @@ def load() -> C.CDLL:
     L.nmch_engine_init_ms.argtypes = [vp]
     L.nmch_engine_init_ms.restype = C.c_float
     L.nmch_engine_launch_info.argtypes = [vp, C.POINTER(NmchLaunchInfo)]
+    L.nmch_group_create.argtypes = [C.POINTER(NmchParams), C.c_int, C.POINTER(vp)]
+    L.nmch_group_init.argtypes = [vp, C.c_ulonglong]
+    L.nmch_group_set_params.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    L.nmch_group_compute.argtypes = [vp, C.POINTER(NmchMoments)]
+    L.nmch_group_explore.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.POINTER(NmchMoments)]
+    L.nmch_group_finalize.argtypes = [vp]
+    L.nmch_group_destroy.argtypes = [vp]
+    L.nmch_group_destroy.restype = None
+    L.nmch_group_init_ms.argtypes = [vp]
+    L.nmch_group_init_ms.restype = C.c_float
+    L.nmch_group_size.argtypes = [vp]
     L.nmch_status_string.argtypes = [C.c_int]
     L.nmch_status_string.restype = C.c_char_p
     L.nmch_last_error.restype = C.c_char_p

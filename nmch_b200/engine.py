@@ -136,3 +136,69 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class Group:
+    """Single-process multi-GPU group (nmch_group_* of the C ABI): paths sharded over n_gpus devices, one
+    ncclAllReduce of the partial moments per compute()/explore()."""
+
+    def __init__(self, n_gpus: int, **kw):
+        self._lib = capi.load()
+        defaults = dict(NTPB=512, NB=512, T=1.0, S_0=1.0, v_0=0.1, r=0.0, k=0.5, rho=-0.7, theta=0.1, sigma=0.3, N=1000,
+                        method=METHOD_FE, floor=FLOOR_ABS, rng=RNG_PHILOX, device=-1, n_paths=0, first_path=0, n_local=0,
+                        paths_per_thread=0, block_threads=0)
+        defaults.update(kw)
+        self.params = capi.NmchParams(*[defaults[n] for n, _ in capi.NmchParams._fields_])
+        self._h = C.c_void_p()
+        capi.check(self._lib.nmch_group_create(C.byref(self.params), n_gpus, C.byref(self._h)))
+
+    def init(self, seed: int = 1234) -> "Group":
+        capi.check(self._lib.nmch_group_init(self._h, seed))
+        return self
+
+    def set_params(self, k, theta, sigma) -> None:
+        capi.check(self._lib.nmch_group_set_params(self._h, k, theta, sigma))
+
+    def compute(self) -> Moments:
+        m = capi.NmchMoments()
+        capi.check(self._lib.nmch_group_compute(self._h, C.byref(m)))
+        return Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms)
+
+    def explore(self, k, theta, sigma):
+        k = np.ascontiguousarray(k, np.float32)
+        theta = np.ascontiguousarray(theta, np.float32)
+        sigma = np.ascontiguousarray(sigma, np.float32)
+        out = (capi.NmchMoments * len(k))()
+        f32p = C.POINTER(C.c_float)
+        capi.check(self._lib.nmch_group_explore(self._h, k.ctypes.data_as(f32p), theta.ctypes.data_as(f32p),
+                                                sigma.ctypes.data_as(f32p), len(k), out))
+        return [Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms) for m in out]
+
+    @property
+    def size(self) -> int:
+        return self._lib.nmch_group_size(self._h)
+
+    @property
+    def init_ms(self) -> float:
+        return self._lib.nmch_group_init_ms(self._h)
+
+    def finalize(self) -> None:
+        if self._h:
+            capi.check(self._lib.nmch_group_finalize(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.nmch_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,118 @@
+// nmch.cpp -- the `NMCH` command line tool: same flags, defaults, output text and exit codes as the reference
+// (src/NMCH/test/nmch.cu:49-139), host C++ over the method API.  Additive flags (defaults = reference behaviour):
+//   --g abs|plus        variance floor (README.md:37-40; the reference codes only abs)
+//   --rng philox|xorwow|philox-compat   generator tag / stream mode (reference CLI: Philox, nmch.cu:119,130)
+//   --gpus N            shard the paths over N GPUs, one NCCL allreduce of the moments
+//   --paths-per-thread P, --json (one machine-readable line after the report)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "NMCH/methods/NMCH_EM.hpp"
+#include "NMCH/methods/NMCH_FE.hpp"
+
+using namespace nmch::methods;
+
+namespace {
+
+struct Options {
+    int NTPB = 512, NB = 512, N = 1000, gpus = 1, ppt = 0;
+    float T = 1.0f, S_0 = 1.0f, v_0 = 0.1f, r = 0.0f, k = 0.5f, rho = -0.7, theta = 0.1f, sigma = 0.3f;
+    unsigned long long seed = 1234;
+    std::string method = "fe", g = "abs", rng = "philox";
+    bool json = false;
+};
+
+void usage(const char *argv0)
+{
+    // the reference's help text, stale defaults included (nmch.cu:94-111), then the additive flags
+    printf("Usage: %s [options]\n", argv0);
+    printf("Options:\n");
+    printf("  --NTPB <int>       Number of threads per block (default: 1024)\n");
+    printf("  --NB <int>         Number of blocks (default: 512)\n");
+    printf("  --T <float>        Time period (default: 1.0)\n");
+    printf("  --S_0 <float>      Initial stock price (default: 1.0)\n");
+    printf("  --v_0 <float>      Initial volatility (default: 0.1)\n");
+    printf("  --r <float>        Risk-free rate (default: 0.0)\n");
+    printf("  --k <float>        Mean reversion rate (default: 0.5)\n");
+    printf("  --rho <float>      Correlation (default: -0.7)\n");
+    printf("  --theta <float>    Long-term volatility (default: 0.1)\n");
+    printf("  --sigma <float>    Volatility of volatility (default: 0.3)\n");
+    printf("  --N <int>          Number of time steps (default: 50)\n");
+    printf("  --seed <ull>       Random seed (default: 1234)\n");
+    printf("  --method <string>  Method to use: fe or em (default: fe)\n");
+    printf("  --help             Display this help message\n");
+    printf("B200 engine options (actual defaults: NTPB 512, NB 512, N 1000):\n");
+    printf("  --g <abs|plus>     Variance floor g(.) (default: abs)\n");
+    printf("  --rng <philox|xorwow|philox-compat>  Stream mode (default: philox)\n");
+    printf("  --gpus <int>       GPUs to shard the paths over (default: 1)\n");
+    printf("  --paths-per-thread <int>  1, 2, 4 or 8 (default: auto)\n");
+    printf("  --json             Also print one JSON line with the raw moments\n");
+}
+
+template <typename M>
+int run(const Options &o)
+{
+    M m(o.NTPB, o.NB, o.T, o.S_0, o.v_0, o.r, o.k, o.rho, o.theta, o.sigma, o.N);
+    m.set_floor_plus(o.g == "plus");
+    m.set_gpus(o.gpus);
+    m.set_philox_compat(o.rng == "philox-compat");
+    m.set_paths_per_thread(o.ppt);
+    m.init(o.seed);
+    m.compute();
+    m.print_stats();
+    if (o.json) {
+        const double n = (double)o.NTPB * (double)o.NB;
+        const double units = o.method == "fe" ? n * o.N : n;
+        printf("{\"method\": \"%s\", \"rng\": \"%s\", \"floor\": \"%s\", \"gpus\": %d, \"n_paths\": %.0f, \"N\": %d, "
+               "\"sum_payoff\": %.17g, \"sum_payoff_sq\": %.17g, \"E\": %.9g, \"E2\": %.9g, \"std_error\": %.6g, "
+               "\"err\": %.9g, \"exec_ms\": %.6f, \"%s\": %.6g}\n",
+               o.method.c_str(), o.rng.c_str(), o.g.c_str(), o.gpus, n, o.N, m.get_sum_payoff(), m.get_sum_payoff_sq(),
+               m.get_strike_price(), m.get_price_squared(), m.get_std_error(), m.get_err(), m.get_execution_time(),
+               o.method == "fe" ? "path_steps_per_s" : "paths_per_s", units / (m.get_execution_time() * 1e-3));
+    }
+    m.finalize();
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    Options o;
+    for (int i = 1; i < argc; ++i) {
+        auto has = [&](const char *f) { return strcmp(argv[i], f) == 0 && i + 1 < argc; };
+        if (has("--NTPB")) o.NTPB = atoi(argv[++i]);
+        else if (has("--NB")) o.NB = atoi(argv[++i]);
+        else if (has("--T")) o.T = atof(argv[++i]);
+        else if (has("--S_0")) o.S_0 = atof(argv[++i]);
+        else if (has("--v_0")) o.v_0 = atof(argv[++i]);
+        else if (has("--r")) o.r = atof(argv[++i]);
+        else if (has("--k")) o.k = atof(argv[++i]);
+        else if (has("--rho")) o.rho = atof(argv[++i]);
+        else if (has("--theta")) o.theta = atof(argv[++i]);
+        else if (has("--sigma")) o.sigma = atof(argv[++i]);
+        else if (has("--N")) o.N = atoi(argv[++i]);
+        else if (has("--seed")) o.seed = strtoull(argv[++i], nullptr, 10);
+        else if (has("--method")) o.method = argv[++i];
+        else if (has("--g")) o.g = argv[++i];
+        else if (has("--rng")) o.rng = argv[++i];
+        else if (has("--gpus")) o.gpus = atoi(argv[++i]);
+        else if (has("--paths-per-thread")) o.ppt = atoi(argv[++i]);
+        else if (strcmp(argv[i], "--json") == 0) o.json = true;
+        else if (strcmp(argv[i], "--help") == 0) { usage(argv[0]); return 0; }
+    }
+    if (o.rng != "philox" && o.rng != "xorwow" && o.rng != "philox-compat") {
+        printf("Unknown rng: %s\n", o.rng.c_str());
+        return 1;
+    }
+    const bool x = o.rng == "xorwow";
+    if (o.method == "fe")
+        return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(o);
+    if (o.method == "em")
+        return x ? run<NMCH_EM_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_EM_K3_MM<curandStatePhilox4_32_10_t>>(o);
+    printf("Unknown method: %s\n", o.method.c_str());      // reference nmch.cu:135-137
+    return 1;
+}

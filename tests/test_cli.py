@@ -1,0 +1,115 @@
+"""The NMCH / exploration command line tools (C++ over the method API over the C ABI)."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NMCH = os.path.join(ROOT, "bin", "NMCH")
+EXPL = os.path.join(ROOT, "bin", "exploration")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from nmch_b200 import _build
+    _build.build_cli()
+    assert os.path.exists(NMCH) and os.path.exists(EXPL)
+
+
+def run(exe, *args):
+    return subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=900)
+
+
+def test_help_and_unknown_method_exit_codes():
+    r = run(NMCH, "--help")
+    assert r.returncode == 0 and "--method <string>  Method to use: fe or em (default: fe)" in r.stdout   # nmch.cu:94-111
+    r = run(NMCH, "--method", "heun")
+    assert r.returncode == 1 and r.stdout.strip() == "Unknown method: heun"                                # nmch.cu:135-137
+    assert run(EXPL, "--help").returncode == 0
+
+
+def test_error_convention_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = run(NMCH, "--NB", 8)
+    assert r.returncode == 1
+    assert re.search(r"There is an error in file .* at line \d+", r.stdout)     # utils.cu:30-35
+    assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,title", [("fe", "FORWARD-EULER"), ("em", "EXACT-METHOD")])
+def test_nmch_report_matches_reference_format(method, title):
+    r = run(NMCH, "--method", method, "--NB", 64, "--N", 200, "--json")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    want = ["Base parameters:", "NTPB    = 512", "NB      = 64", "T       = 1.000000", "S_0,K   = 1.000000",
+            "v_0     = 0.100000", "r       = 0.000000", "k       = 0.500000", "theta   = 0.100000",
+            "sigma   = 0.300000", "N       = 200", "dt      = 0.005000", f"METHOD: {title}"]
+    assert lines[:13] == want
+    assert lines[13].startswith("The estimated price E[X] is equal to ")
+    assert lines[14].startswith("The estimated E[X^2] is equal to ")
+    assert lines[15] == "The true price 0.119235"                                   # Black-Scholes line, NMCH_FE.cu:336-338
+    assert lines[16].startswith("error associated to a confidence interval of 95% = ")
+    assert lines[17].startswith("Execution time ") and lines[17].endswith(" ms")
+    assert lines[18].startswith("Initialization time ")
+    j = json.loads(lines[19])
+    from nmch_b200 import engine as E
+    with E.Engine(NTPB=512, NB=64, N=200, method=E.METHOD_FE if method == "fe" else E.METHOD_EM) as e:
+        e.init(1234)
+        m = e.compute()
+    assert j["sum_payoff"] == m.sum_payoff and j["sum_payoff_sq"] == m.sum_payoff_sq
+    assert abs(float(lines[13].split()[-1]) - m.mean) < 1e-6
+
+
+@pytest.mark.gpu
+def test_nmch_xorwow_tag_matches_reference_binary():
+    from oracle import oracle as o
+    if not os.path.exists(o.REF_HARNESS_PATH):
+        pytest.skip("reference harness not shipped")
+    r = run(NMCH, "--rng", "xorwow", "--NB", 128, "--N", 300, "--json")
+    j = json.loads(r.stdout.splitlines()[-1])
+    ref = json.loads(run(o.REF_HARNESS_PATH, "--method", "fe", "--rng", "xorwow", "--NB", 128, "--N", 300).stdout.splitlines()[0])
+    assert abs(j["E"] - ref["E"]) / ref["E"] < 1e-5
+    assert abs(j["err"] - ref["err"]) / ref["err"] < 1e-4          # the reference's own CI formula, same inputs
+
+
+@pytest.mark.gpu
+def test_exploration_default_run_is_the_reference_sweep():
+    from oracle import oracle as o
+    r = run(EXPL, "--N", 40)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "method, k, theta, sigma, execution_time, err"              # exploration.cu:69
+    fe = [l.split(", ") for l in lines[1:] if l.startswith("fe")]
+    em = [l.split(", ") for l in lines[1:] if l.startswith("em")]
+    k, th, sg = o.exploration_grid(5, apply_filter=True)
+    assert len(fe) == len(em) == len(k) == 200
+    np.testing.assert_allclose([float(x[1]) for x in fe], k, atol=1e-6)
+    np.testing.assert_allclose([float(x[3]) for x in fe], sg, atol=1e-6)
+    # same err column as the reference build for the first points (XORWOW tag, continued streams, N = 40)
+    if os.path.exists(o.REF_HARNESS_PATH):
+        pts = os.path.join(ROOT, "gpurun_out", "_sweep_pts.txt")
+        os.makedirs(os.path.dirname(pts), exist_ok=True)
+        with open(pts, "w") as f:
+            f.write("0.5 0.1 0.3\n")                                                 # the warm-up compute
+            for i in range(8):
+                f.write(f"{k[i]:.9g} {th[i]:.9g} {sg[i]:.9g}\n")
+        ref = [json.loads(l) for l in run(o.REF_HARNESS_PATH, "--method", "fe", "--rng", "xorwow", "--NTPB", 512, "--NB", 10,
+                                          "--N", 40, "--points", pts).stdout.splitlines()][1:]
+        for i in range(8):
+            assert abs(float(fe[i][5]) - ref[i]["err"]) <= 2e-6 + 1e-4 * ref[i]["err"], (i, fe[i], ref[i]["err"])
+
+
+@pytest.mark.gpu
+def test_exploration_bias_column_and_linspace_grid():
+    r = run(EXPL, "--points", 3, "--log2-paths", 16, "--N", 100, "--rng", "philox", "--method", "fe", "--bias")
+    assert r.returncode == 0, r.stderr
+    rows = [l.split(", ") for l in r.stdout.splitlines()[1:]]
+    assert r.stdout.splitlines()[0].endswith(", bias")
+    assert 20 <= len(rows) <= 27
+    assert all(abs(float(x[6])) < 0.01 for x in rows)          # Euler bias + MC noise stay small
