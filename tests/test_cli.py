@@ -107,9 +107,10 @@ def test_exploration_default_run_is_the_reference_sweep():
 
 @pytest.mark.gpu
 def test_exploration_bias_column_and_linspace_grid():
-    r = run(EXPL, "--points", 3, "--log2-paths", 16, "--N", 100, "--rng", "philox", "--method", "fe", "--bias")
+    r = run(EXPL, "--points", 3, "--log2-paths", 16, "--N", 400, "--rng", "philox", "--method", "fe", "--bias")
     assert r.returncode == 0, r.stderr
     rows = [l.split(", ") for l in r.stdout.splitlines()[1:]]
     assert r.stdout.splitlines()[0].endswith(", bias")
     assert 20 <= len(rows) <= 27
-    assert all(abs(float(x[6])) < 0.01 for x in rows)          # Euler bias + MC noise stay small
+    worst = max(rows, key=lambda x: abs(float(x[6])))
+    assert abs(float(worst[6])) < 0.03, worst                  # Euler bias (sigma = 1 corners) + MC noise stay small
