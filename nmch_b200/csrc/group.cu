@@ -197,10 +197,24 @@ int nmch_group_init(nmch_group_t *g, unsigned long long seed)
         ncclResult_t r = g_nccl.CommInitAll(g->comm.data(), g->n, g->dev.data());
         if (r != ncclSuccess) return nccl_fail("ncclCommInitAll", r);
     }
-    cudaSetDevice(prev);
     g->init_ms = ms;
     g->inited = true;
     int rc = ensure_moments(g, 1);
+    if (rc == NMCH_OK && g->n > 1) {
+        // first collective on a communicator sets up its channels (~100 ms): pay that here, not in compute()
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int i = 0; i < g->n && r == ncclSuccess; ++i) {
+            cudaSetDevice(g->dev[i]);
+            cudaMemsetAsync(g->d_mom[i], 0, 2 * sizeof(double), g->stream[i]);
+            r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], 2, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
+        }
+        if (r == ncclSuccess) r = g_nccl.GroupEnd();
+        if (r != ncclSuccess) return nccl_fail("NCCL warm-up allreduce", r);
+        for (int i = 0; i < g->n; ++i) {
+            cudaSetDevice(g->dev[i]);
+            cudaStreamSynchronize(g->stream[i]);
+        }
+    }
     cudaSetDevice(prev);
     return rc;
 }
