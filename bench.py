@@ -188,16 +188,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        times = []
+        times, walls = [], []
         base = None
         for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
             base = cpu_baseline(args.method, N, budget_s=max(2.0, 60.0 / max(1, args.steps + args.warmup)))
             if i >= args.warmup:
                 times.append(base["value"])
+                walls.append(time.perf_counter() - t0)
         v = sum(times) / len(times)
         base["value"] = v
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "edo01/NMCH is CUDA-only; its hot loop restated in C (oracle/) is what runs on the host cores"}
@@ -217,6 +219,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from nmch_b200.distributed import ShardedEngine

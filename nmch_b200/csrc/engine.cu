@@ -65,12 +65,13 @@ namespace {
 
 bool is_pow2_or_mult(unsigned long long v, unsigned long long m) { return (v % m) == 0ull; }
 
-int pick_paths_per_thread(const nmch_engine *e)
+int pick_paths_per_thread(const nmch_engine *e, int n_points)
 {
     if (e->p.paths_per_thread > 0) return e->p.paths_per_thread;
     // Enough warps first (>= 16 resident per SM), then ILP: each extra path per thread hides more of
-    // the dependent MUFU/FMA chain without costing occupancy (47 regs at P = 4).
-    const unsigned long long per_sm = e->n_local / (unsigned long long)(e->sm_count > 0 ? e->sm_count : 148);
+    // the dependent MUFU/FMA chain without costing occupancy (47 regs at P = 4).  Work = paths x points.
+    const unsigned long long per_sm = e->n_local * (unsigned long long)n_points /
+                                      (unsigned long long)(e->sm_count > 0 ? e->sm_count : 148);
     if (per_sm >= 4096ull) return 4;
     if (per_sm >= 2048ull) return 2;
     return 1;
@@ -177,7 +178,7 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
     if (p.method == NMCH_METHOD_FE) {
         FeLaunch L;
         if (native) {
-            const int P = e->P, threads = e->threads;
+            const int P = pick_paths_per_thread(e, n_points), threads = e->threads;
             const unsigned long long tile = (unsigned long long)P * threads;
             const unsigned long long tiles = (e->n_local + tile - 1) / tile;
             // keep the per-point partial list short when many points share the launch
@@ -309,7 +310,6 @@ int nmch_engine_init(nmch_engine_t *e, unsigned long long seed)
     e->draw_offset = 0;
     e->em_calls = 0;
     e->threads = e->p.block_threads ? e->p.block_threads : 256;
-    e->P = pick_paths_per_thread(e);
     if (e->p.rng == NMCH_RNG_XORWOW_COMPAT) {
         const size_t n = (size_t)e->n_local;
         CU_TRY(xorwow_tables_create(&e->xtab));
