@@ -58,9 +58,10 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
+    path = os.environ.get("NMCH_B200_LIB") or _build.LIB     # override: tuning builds of the same ABI
+    if path == _build.LIB and not os.path.exists(path):
         _build.build()
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(path)
     vp, f32p, f64p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double)
     L.nmch_engine_create.argtypes = [C.POINTER(NmchParams), C.POINTER(vp)]
     L.nmch_engine_init.argtypes = [vp, C.c_ulonglong]

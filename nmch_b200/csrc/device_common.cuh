@@ -56,6 +56,53 @@ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
     return U4{c0, c1, c2, c3};
 }
 
+// The same block function with the loop-invariant part factored out by hand, for a loop that walks the low
+// counter word c0 while (c1, c2, c3) = (block_hi, path_lo, path_hi) stay fixed:
+//   round 1:  p1 = M1*c2 is invariant;  p0 = M0*c0 is shared by all paths of the thread
+//   round 2:  its c0 = hi(p1)^c1^k0[0] is invariant, so the product M0*c0 is too
+// PhiloxPathInv holds the three invariant words of one path; the opaque asm pins them in registers (ptxas
+// otherwise rematerialises them every iteration under the register cap: +14 instructions per 8 path-steps).
+struct PhiloxPathInv {
+    uint32_t lo1;        // lo(M1 * path_lo): c1 entering round 2
+    uint32_t q_hi, q_lo; // M0 * (hi(M1*path_lo) ^ block_hi ^ k0[0]): the round-2 multiply on c0
+};
+
+__device__ __forceinline__ PhiloxPathInv philox_path_invariants(uint32_t block_hi, uint32_t path_lo, const PhiloxKeys &K)
+{
+    const unsigned long long p1 = (unsigned long long)kPhiloxM1 * path_lo;
+    const uint32_t c0 = (uint32_t)(p1 >> 32) ^ block_hi ^ K.k0[0];
+    const unsigned long long q = (unsigned long long)kPhiloxM0 * c0;
+    PhiloxPathInv v{(uint32_t)p1, (uint32_t)(q >> 32), (uint32_t)q};
+    asm volatile("" : "+r"(v.lo1), "+r"(v.q_hi), "+r"(v.q_lo));
+    return v;
+}
+
+// s_hi:s_lo = M0 * block_lo (computed once per thread and iteration), path_hi as in the counter.
+__device__ __forceinline__ U4 philox4x32_10_hoisted(uint32_t s_hi, uint32_t s_lo, uint32_t path_hi,
+                                                    const PhiloxPathInv &inv, const PhiloxKeys &K)
+{
+    // state after round 1: (c0, c1, c2, c3) = (hi1^c1^k0[0], lo1, hi0^c3^k1[0], lo0)
+    //   -> round 2 needs M0*c0 (= inv.q) and M1*c2 with c2 = s_hi ^ path_hi ^ k1[0] (shared by the thread's paths)
+    const uint32_t c2_r1 = s_hi ^ path_hi ^ K.k1[0];
+    const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2_r1;
+    uint32_t c0 = (uint32_t)(p1 >> 32) ^ inv.lo1 ^ K.k0[1];
+    uint32_t c1 = (uint32_t)p1;
+    uint32_t c2 = inv.q_hi ^ s_lo ^ K.k1[1];
+    uint32_t c3 = inv.q_lo;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+        const unsigned long long a = (unsigned long long)kPhiloxM0 * c0;
+        const unsigned long long b = (unsigned long long)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(b >> 32) ^ c1 ^ K.k0[r];
+        const uint32_t n2 = (uint32_t)(a >> 32) ^ c3 ^ K.k1[r];
+        c1 = (uint32_t)b;
+        c3 = (uint32_t)a;
+        c0 = n0;
+        c2 = n2;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
 // ---------------------------------------------------------------------------------------
 // Single-instruction transcendental wrappers (MUFU.*).  .ftz keeps ptxas from wrapping them in
 // denormal-scaling sequences; every argument in the kernels is a normal number by construction.

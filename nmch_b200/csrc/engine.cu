@@ -309,7 +309,7 @@ int nmch_engine_init(nmch_engine_t *e, unsigned long long seed)
     e->seed = seed;
     e->draw_offset = 0;
     e->em_calls = 0;
-    e->threads = e->p.block_threads ? e->p.block_threads : 256;
+    e->threads = e->p.block_threads ? e->p.block_threads : 128;
     if (e->p.rng == NMCH_RNG_XORWOW_COMPAT) {
         const size_t n = (size_t)e->n_local;
         CU_TRY(xorwow_tables_create(&e->xtab));

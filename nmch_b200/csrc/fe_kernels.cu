@@ -38,8 +38,19 @@ __device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, 
     V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
 }
 
+// Resident blocks per SM the register allocator must leave room for (measured sweep, profiles/r01_fe_variants.txt):
+// 48 registers at P = 4 keeps 40 warps per SM in flight, which beats both more ILP and more occupancy.
+template <int P, int THREADS>
+struct FeOccupancy {
+#ifndef NMCHB_FE_WARPS_P4
+#define NMCHB_FE_WARPS_P4 40
+#endif
+    static constexpr int kWarpsTarget = (P <= 2) ? 48 : (P == 4 ? NMCHB_FE_WARPS_P4 : 24);
+    static constexpr int kMinBlocks = kWarpsTarget * 32 / THREADS;
+};
+
 template <int P, int FLOOR, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, FeOccupancy<P, THREADS>::kMinBlocks)
 fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ pts, ReduceBuffers rb,
                  float *__restrict__ S_out, float *__restrict__ V_out)
 {
@@ -52,7 +63,9 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
     const unsigned long long w0 = L.draw_offset + (unsigned long long)point * 2ull * (unsigned long long)L.N;
     const bool half_start = (w0 & 2ull) != 0ull;
 
-    double acc = 0.0, acc2 = 0.0;
+    // per-thread FP64 payoff sums live in shared memory between tiles, not in registers across the step loop
+    __shared__ double2 s_acc[THREADS];
+    s_acc[threadIdx.x] = make_double2(0.0, 0.0);
     for (int t = 0; t < L.tiles_per_block; ++t) {
         const unsigned long long tile = (unsigned long long)blockIdx.x * L.tiles_per_block + t;
         const unsigned long long local0 = tile * TILE;
@@ -78,16 +91,30 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
             ++blk;
             --n;
         }
-        const int pairs = n >> 1;
-#pragma unroll 1
-        for (int it = 0; it < pairs; ++it) {
+        // Full blocks, two steps each.  The loop is split where the low counter word would wrap so that the
+        // high word is loop-invariant: Philox round 1 and the per-path multiply of round 2 then depend only on
+        // (path, high word) and are hoisted; the multiplies on the low word are shared by the thread's P paths.
+        int pairs = n >> 1;
+        while (pairs > 0) {
+            const uint32_t blk_hi = (uint32_t)(blk >> 32);
+            const uint32_t blk_lo = (uint32_t)blk;
+            const unsigned long long room = 0x100000000ull - (unsigned long long)blk_lo;
+            const int chunk = ((unsigned long long)pairs < room) ? pairs : (int)room;
+            PhiloxPathInv inv[P];
 #pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
-                fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
-                fe_step_native<FLOOR>(S[j], V[j], w.z, w.w, crdt, zr, zc, pc);
+            for (int j = 0; j < P; ++j) inv[j] = philox_path_invariants(blk_hi, path_lo0 + j * THREADS, L.keys);
+#pragma unroll 1
+            for (int it = 0; it < chunk; ++it) {
+                const unsigned long long s = (unsigned long long)kPhiloxM0 * (blk_lo + (uint32_t)it);   // uniform datapath
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const U4 w = philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv[j], L.keys);
+                    fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
+                    fe_step_native<FLOOR>(S[j], V[j], w.z, w.w, crdt, zr, zc, pc);
+                }
             }
-            ++blk;
+            blk += (unsigned long long)chunk;
+            pairs -= chunk;
         }
         if (n & 1) {
 #pragma unroll
@@ -96,21 +123,24 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
                 fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
             }
         }
+        double2 acc = s_acc[threadIdx.x];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             const unsigned long long idx = local0 + (unsigned long long)(j * THREADS) + threadIdx.x;
             if (idx < L.n_local) {
                 const double pay = (double)fmaxf(0.0f, S[j] - L.K);
-                acc += pay;
-                acc2 += pay * pay;
+                acc.x += pay;
+                acc.y += pay * pay;
                 if (S_out != nullptr && point == L.n_points - 1) {
                     S_out[idx] = S[j];
                     V_out[idx] = V[j];
                 }
             }
         }
+        s_acc[threadIdx.x] = acc;
     }
-    block_reduce_and_finish(acc, acc2, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+    const double2 total = s_acc[threadIdx.x];
+    block_reduce_and_finish(total.x, total.y, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
 }
 
 template <int P, int FLOOR>

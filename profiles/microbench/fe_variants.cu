@@ -1,0 +1,167 @@
+// fe_variants.cu -- standalone throughput experiments on variants of the native FE step loop (not product code).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I ../../nmch_b200/csrc -o fe_variants fe_variants.cu
+// Each variant simulates 2^24 paths x 1000 steps and prints path-steps/s and the mean payoff (sanity).
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+
+using namespace nmchb;
+
+struct Consts {
+    PhiloxKeys keys;
+    float crdt, zr, zc, va, vb, vs, S0, v0, K;
+    int N;
+};
+
+template <int MODE>
+__device__ __forceinline__ void step(float &S, float &V, uint32_t wa, uint32_t wb, const Consts &c)
+{
+    const float f1 = bits_to_1_2(wa);
+    const float f2 = bits_to_1_2(wb);
+    const float u = f1 - 0.99999994f;
+    const float l2 = lg2_approx(u);
+    const float q = sqrt_approx(-(V * l2));
+    const float ang = f2 * 6.2831855f;
+    const float gs = q * sin_approx(ang);
+    const float gc = q * cos_approx(ang);
+    float m = fmaf(gs, c.zr, c.crdt);
+    m = fmaf(gc, c.zc, m);
+    S *= m;
+    float vn = fmaf(V, c.va, c.vb);
+    vn = fmaf(gs, c.vs, vn);
+    if (MODE == 0) V = fabsf(vn);
+    else if (MODE == 1) V = fmaxf(vn, 0.0f);
+    else V = __uint_as_float(__float_as_uint(vn) & 0x7fffffffu);   // abs on the ALU pipe
+}
+
+// uniform from already-spliced float bits (dense variant)
+template <int MODE>
+__device__ __forceinline__ void step_f(float &S, float &V, float f1, float f2, const Consts &c)
+{
+    const float u = f1 - 0.99999994f;
+    const float l2 = lg2_approx(u);
+    const float q = sqrt_approx(-(V * l2));
+    const float ang = f2 * 6.2831855f;
+    const float gs = q * sin_approx(ang);
+    const float gc = q * cos_approx(ang);
+    float m = fmaf(gs, c.zr, c.crdt);
+    m = fmaf(gc, c.zc, m);
+    S *= m;
+    float vn = fmaf(V, c.va, c.vb);
+    vn = fmaf(gs, c.vs, vn);
+    V = (MODE == 1) ? fmaxf(vn, 0.0f) : fabsf(vn);
+}
+
+// VARIANT 0: product loop (2 steps / block).  1: dense (5 steps / 2 blocks).  2: product loop unrolled x2.
+template <int P, int THREADS, int MINB, int VARIANT, int MODE>
+__global__ void __launch_bounds__(THREADS, MINB) fe(const __grid_constant__ Consts c, double *out)
+{
+    const uint32_t path0 = blockIdx.x * (P * THREADS) + threadIdx.x;
+    float S[P], V[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) { S[j] = c.S0; V[j] = c.v0; }
+    uint32_t blk = 0;
+    if (VARIANT == 0) {
+#pragma unroll 1
+        for (int it = 0; it < c.N / 2; ++it) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10(blk, 0u, path0 + j * THREADS, 0u, c.keys);
+                step<MODE>(S[j], V[j], w.x, w.y, c);
+                step<MODE>(S[j], V[j], w.z, w.w, c);
+            }
+            ++blk;
+        }
+    } else if (VARIANT == 2) {
+#pragma unroll 2
+        for (int it = 0; it < c.N / 2; ++it) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10(blk, 0u, path0 + j * THREADS, 0u, c.keys);
+                step<MODE>(S[j], V[j], w.x, w.y, c);
+                step<MODE>(S[j], V[j], w.z, w.w, c);
+            }
+            ++blk;
+        }
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < c.N / 5; ++it) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 a = philox4x32_10(blk, 0u, path0 + j * THREADS, 0u, c.keys);
+                const U4 b = philox4x32_10(blk + 1, 0u, path0 + j * THREADS, 0u, c.keys);
+                // 8 uniforms from the top 23 bits, 2 more from the 9 low bits of 3 words each (27 -> 23 bits)
+                const uint32_t e0 = ((a.x & 0x1ffu) << 14) | ((a.y & 0x1ffu) << 5) | ((a.z & 0x1ffu) >> 4);
+                const uint32_t e1 = ((b.x & 0x1ffu) << 14) | ((b.y & 0x1ffu) << 5) | ((b.z & 0x1ffu) >> 4);
+                step<MODE>(S[j], V[j], a.x, a.y, c);
+                step<MODE>(S[j], V[j], a.z, a.w, c);
+                step<MODE>(S[j], V[j], b.x, b.y, c);
+                step<MODE>(S[j], V[j], b.z, b.w, c);
+                step_f<MODE>(S[j], V[j], __uint_as_float(e0 | 0x3f800000u), __uint_as_float(e1 | 0x3f800000u), c);
+            }
+            blk += 2;
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc += (double)fmaxf(S[j] - c.K, 0.0f);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+template <int P, int THREADS, int MINB, int VARIANT, int MODE>
+void run(const char *name, const Consts &c, double *d_out)
+{
+    const unsigned n = 1u << 24;
+    const unsigned blocks = n / (P * THREADS);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, fe<P, THREADS, MINB, VARIANT, MODE>);
+    float best = 1e30f;
+    double sum = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaMemset(d_out, 0, 8);
+        cudaEventRecord(e0);
+        fe<P, THREADS, MINB, VARIANT, MODE><<<blocks, THREADS>>>(c, d_out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+        cudaMemcpy(&sum, d_out, 8, cudaMemcpyDeviceToHost);
+    }
+    printf("%-46s P=%d T=%3d minb=%d regs=%3d  %7.3f ms  %.4e path-steps/s  E=%.6f\n", name, P, THREADS, MINB, attr.numRegs, best,
+           (double)n * c.N / (best * 1e-3), sum / n);
+}
+
+int main()
+{
+    Consts c;
+    c.keys = philox_expand_keys(1234);
+    const float dt = 1e-3f, c0 = 1.17741002f, rho = -0.7f;
+    c.crdt = 1.0f; c.zr = rho * sqrtf(dt) * c0; c.zc = sqrtf(1 - rho * rho) * sqrtf(dt) * c0;
+    c.va = 1.0f - 0.5f * dt; c.vb = 0.5f * 0.1f * dt; c.vs = 0.3f * sqrtf(dt) * c0;
+    c.S0 = 1.0f; c.v0 = 0.1f; c.K = 1.0f; c.N = 1000;
+    double *d_out;
+    cudaMalloc(&d_out, 8);
+    run<4, 256, 1, 0, 0>("product loop", c, d_out);
+    run<4, 128, 1, 0, 0>("product loop", c, d_out);
+    run<4, 128, 10, 0, 0>("product loop, minblocks 10 (<=48 regs)", c, d_out);
+    run<4, 128, 12, 0, 0>("product loop, minblocks 12 (<=40 regs)", c, d_out);
+    run<4, 64, 20, 0, 0>("product loop, 64 threads minblocks 20", c, d_out);
+    run<4, 256, 5, 0, 0>("product loop, 256 threads minblocks 5", c, d_out);
+    run<4, 128, 10, 2, 0>("unroll x2, minblocks 10", c, d_out);
+    run<4, 128, 8, 2, 0>("unroll x2, minblocks 8", c, d_out);
+    run<2, 128, 16, 2, 0>("unroll x2, P=2 minblocks 16", c, d_out);
+    run<2, 128, 12, 2, 0>("unroll x2, P=2 minblocks 12", c, d_out);
+    run<2, 128, 12, 0, 0>("product loop, P=2 minblocks 12", c, d_out);
+    run<8, 128, 5, 0, 0>("product loop, P=8 minblocks 5", c, d_out);
+    run<8, 128, 6, 0, 0>("product loop, P=8 minblocks 6", c, d_out);
+    run<4, 128, 10, 0, 1>("(.)+ floor, minblocks 10", c, d_out);
+    run<4, 128, 10, 1, 0>("dense, minblocks 10", c, d_out);
+    run<2, 128, 12, 1, 0>("dense, P=2 minblocks 12", c, d_out);
+    return 0;
+}
