@@ -267,3 +267,66 @@ def test_lifecycle_errors():
     with pytest.raises(capi.NmchError):
         e.compute()
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: 64-bit path indices and seeds, general r / S_0 / T, single step, size-independent checks
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rng_e,rng_o,tol", [(0, o.RNG_PHILOX, 2e-3), (2, o.RNG_PHILOX, 2e-4), (1, o.RNG_XORWOW, 2e-4)])
+def test_paths_beyond_2_pow_32_and_64_bit_seed(rng_e, rng_o, tol):
+    first = (1 << 33) + 3 * 4096                      # generator subsequence needs the high counter word
+    seed = 0xDEADBEEFCAFEF00D
+    n, N = 2048, 60
+    with E.Engine(NTPB=1, NB=1, N=N, rng=rng_e, n_paths=first + n, first_path=first, n_local=n) as e:
+        e.init(seed)
+        S, V, m = e.compute_paths()
+    ref = o.fe_run(o.Params(N=N), rng=rng_o, seed=seed, first_path=first, n_paths=n, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=tol, atol=tol / 10)
+    assert abs(m.mean - ref["mean"]) < 10 * tol * 0.2
+
+
+@pytest.mark.parametrize("rng_e,rng_o,tol", [(0, o.RNG_PHILOX, 3e-3), (1, o.RNG_XORWOW, 2e-4)])
+def test_general_rate_spot_maturity(rng_e, rng_o, tol):
+    kw = dict(T=0.5, S_0=2.0, v_0=0.04, r=0.03, k=1.5, rho=0.3, theta=0.09, sigma=0.5)
+    n, N = 4096, 125
+    with E.Engine(NTPB=512, NB=n // 512, N=N, rng=rng_e, **kw) as e:
+        e.init(42)
+        S, V, m = e.compute_paths()
+    ref = o.fe_run(o.Params(N=N, **kw), rng=rng_o, seed=42, n_paths=n, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(V, ref["V"], rtol=10 * tol, atol=tol)
+    # payoff is (S_T - S_0)^+ : strike = spot (NMCH.cu:7)
+    assert abs(m.sum_payoff - np.maximum(S.astype(np.float64) - 2.0, 0).sum()) < 1e-6 * n
+
+
+@pytest.mark.parametrize("rng", [0, 1, 2])
+def test_single_step_and_single_path(rng):
+    with E.Engine(NTPB=1, NB=1, N=1, rng=rng) as e:
+        e.init(1234)
+        S, V, m = e.compute_paths()
+    ref = o.fe_run(o.Params(N=1), rng=o.RNG_XORWOW if rng == 1 else o.RNG_PHILOX, n_paths=1, want_paths=True)
+    np.testing.assert_allclose(S, ref["S"], rtol=1e-5)
+    np.testing.assert_allclose(V, ref["V"], rtol=1e-4)
+    if rng == 1:                                       # SURVEY.md §8c pin: path 0 after one step
+        np.testing.assert_allclose([S[0], V[0]], [0.420270562, 0.17408967], rtol=1e-5)
+
+
+def test_full_size_properties_2_pow_24():
+    # BASELINE configs[1] size: checks that do not need an oracle run of that size
+    n = 1 << 24
+    with E.Engine(NTPB=512, NB=n // 512, N=1000, rng=0) as e:
+        e.init(1234)
+        a = e.compute()
+    with E.Engine(NTPB=512, NB=n // 512, N=1000, rng=0) as e:
+        e.init(1234)
+        b = e.compute()
+    assert a.sum_payoff == b.sum_payoff and a.sum_payoff_sq == b.sum_payoff_sq          # deterministic
+    halves = []
+    for g in range(2):
+        with E.Engine(NTPB=512, NB=n // 512, N=1000, rng=0, first_path=g * n // 2, n_local=n // 2) as e:
+            e.init(1234)
+            halves.append(e.compute())
+    assert abs(halves[0].sum_payoff + halves[1].sum_payoff - a.sum_payoff) < 1e-10 * n   # shards add up
+    assert abs(halves[0].sum_payoff_sq + halves[1].sum_payoff_sq - a.sum_payoff_sq) < 1e-10 * n
+    assert abs(a.mean - o.heston_call()) < 3 * a.std_error + 5e-5                        # price
+    assert 0 < a.variance < a.mean_sq
