@@ -128,12 +128,18 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
 
     float V = L.v0, vI = 0.0f, S = 0.0f;
     if (valid) {
+        // counter = (trial block, stream, path_lo, path_hi): everything but the first word is fixed for this path
+        const PhiloxPathInv inv = philox_path_invariants(stream, path_lo, L.keys);
+        auto next_block = [&](uint32_t b) {
+            const unsigned long long s = (unsigned long long)kPhiloxM0 * b;
+            return philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv, L.keys);
+        };
         uint32_t blk = 0;
         int step = 0;
         bool have_np = false;
         float np = 0.0f;
         while (step < L.N) {
-            const U4 w = philox4x32_10(blk++, stream, path_lo, path_hi, L.keys);
+            const U4 w = next_block(blk++);
             float gsum;
             bool accept;
             if (!MIXED || pc.fast) {
@@ -156,7 +162,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                 accept = false;
                 gsum = 0.0f;
                 if (have_np) {
-                    const U4 w2 = philox4x32_10(blk++, stream, path_lo, path_hi, L.keys);
+                    const U4 w2 = next_block(blk++);
                     float x, unused;
                     box_muller_fast(w2.x, w2.y, x, unused);
                     float shape = pc.d + np, boost = 1.0f;
@@ -180,7 +186,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
             }
         }
         // terminal draw (NMCH_EM.cu:247-260, generalised to S_0, r, T)
-        const U4 w = philox4x32_10(blk, stream, path_lo, path_hi, L.keys);
+        const U4 w = next_block(blk);
         float z, unused;
         box_muller_fast(w.x, w.y, z, unused);
         vI *= L.half_dt;

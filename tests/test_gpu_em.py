@@ -181,3 +181,22 @@ def test_explore_equals_sequential_computes(rng):
             seq.append(e.compute())
     for b, s in zip(batched, seq):
         assert b.sum_payoff == s.sum_payoff and b.sum_payoff_sq == s.sum_payoff_sq
+
+
+def test_full_size_properties_2_pow_22():
+    # BASELINE configs[2] size (EM, N = 1000, 2^22 paths): size-independent checks
+    n = 1 << 22
+    with em_engine(n, 1000) as e:
+        e.init(1234)
+        a = e.compute()
+    with em_engine(n, 1000) as e:
+        e.init(1234)
+        b = e.compute()
+    assert a.sum_payoff == b.sum_payoff and a.sum_payoff_sq == b.sum_payoff_sq          # deterministic
+    halves = []
+    for g in range(2):
+        with E.Engine(NTPB=512, NB=n // 512, N=1000, method=E.METHOD_EM, first_path=g * n // 2, n_local=n // 2) as e:
+            e.init(1234)
+            halves.append(e.compute())
+    assert abs(halves[0].sum_payoff + halves[1].sum_payoff - a.sum_payoff) < 1e-10 * n   # shards add up
+    assert abs(a.mean - o.heston_call()) < 3 * a.std_error                               # unbiased at 8.6e-5
