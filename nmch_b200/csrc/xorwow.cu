@@ -102,14 +102,55 @@ void xorwow_tables_destroy(XorwowSkipTables *t)
     delete t;
 }
 
-// One thread per path.  All lanes of a warp test the same bit index and read the same table row
-// (a broadcast load); only the XOR is predicated on the lane's own state bit.
+// v <- v * M for ONE state held replicated by all 32 lanes of a warp: lane l owns bit l of each of the five
+// words (5 rows, two 16-byte loads each), then the partial XORs are folded with shuffles.
+__device__ __forceinline__ void warp_vecmat(uint32_t v[5], const uint32_t *__restrict__ M, int lane)
+{
+    uint32_t r[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(M + (size_t)(w * 32 + lane) * kRowWords);
+        const uint4 a = __ldg(row);
+        const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t *>(row + 1));
+        const uint32_t mask = 0u - ((v[w] >> lane) & 1u);
+        r[0] ^= a.x & mask; r[1] ^= a.y & mask; r[2] ^= a.z & mask; r[3] ^= a.w & mask; r[4] ^= b4 & mask;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[k] ^= __shfl_xor_sync(0xffffffffu, r[k], o);
+        v[k] = r[k];
+    }
+}
+
+// v <- v * M for a state private to the thread (every lane its own state, and possibly its own matrix).
+__device__ __forceinline__ void thread_vecmat(uint32_t v[5], const uint32_t *__restrict__ M)
+{
+    const uint4 *rows = reinterpret_cast<const uint4 *>(M);
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+        const uint32_t word = v[w];
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const uint4 a = __ldg(rows + 2 * (w * 32 + j));
+            const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t *>(rows + 2 * (w * 32 + j) + 1));
+            const uint32_t mask = 0u - ((word >> j) & 1u);
+            r0 ^= a.x & mask; r1 ^= a.y & mask; r2 ^= a.z & mask; r3 ^= a.w & mask; r4 ^= b4 & mask;
+        }
+    }
+    v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3; v[4] = r4;
+}
+
+// Block of 256 consecutive paths.  When the block's first path is a multiple of 256 all its paths share the
+// digits above bit 8 of the subsequence: warp 0 applies those once for the whole block (cooperative products),
+// and every thread then applies only its own four low digits -- about a third of the work of a full walk.
 __global__ void __launch_bounds__(256)
 xorwow_init_kernel(const uint32_t *__restrict__ tables, unsigned long long seed, unsigned long long first_path,
                    unsigned long long n_local, XorwowState xs)
 {
+    __shared__ uint32_t s_base[5];
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_local) return;
     // seed scramble of XORWOW as cuRAND defines it (curand_kernel.h:807-818)
     const uint32_t s0 = (uint32_t)seed ^ 0xaad26b49u;
     const uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
@@ -118,24 +159,28 @@ xorwow_init_kernel(const uint32_t *__restrict__ tables, unsigned long long seed,
     uint32_t v[5] = {123456789u + t0, 362436069u ^ t0, 521288629u + t1, 88675123u ^ t1, 5783321u + t0};
     const uint32_t d = 6615241u + t1 + t0;
 
+    const unsigned long long block_first = first_path + (unsigned long long)blockIdx.x * blockDim.x;
+    const bool aligned = (block_first & 255ull) == 0ull;          // uniform over the block
     unsigned long long sub = first_path + idx;
-    for (int m = 0; sub != 0ull; ++m, sub >>= 2) {
-        const unsigned q = (unsigned)(sub & 3ull);
-        if (q == 0u) continue;
-        const uint4 *M = reinterpret_cast<const uint4 *>(tables + ((size_t)m * 3 + (q - 1)) * 160 * kRowWords);
-        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-#pragma unroll
-        for (int w = 0; w < 5; ++w) {
-            const uint32_t word = v[w];
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const uint4 a = __ldg(M + 2 * (w * 32 + j));
-                const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t *>(M + 2 * (w * 32 + j) + 1));
-                const uint32_t mask = 0u - ((word >> j) & 1u);
-                r0 ^= a.x & mask; r1 ^= a.y & mask; r2 ^= a.z & mask; r3 ^= a.w & mask; r4 ^= b4 & mask;
+    int m = 0;
+    if (aligned) {
+        if (threadIdx.x < 32) {
+            unsigned long long hi = block_first >> 8;
+            for (int mm = 4; hi != 0ull; ++mm, hi >>= 2) {
+                const unsigned q = (unsigned)(hi & 3ull);
+                if (q != 0u) warp_vecmat(v, tables + ((size_t)mm * 3 + (q - 1)) * 160 * kRowWords, threadIdx.x);
             }
+            if (threadIdx.x < 5) s_base[threadIdx.x] = v[threadIdx.x];
         }
-        v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3; v[4] = r4;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = s_base[k];
+        sub &= 255ull;                                            // the digits still to apply
+    }
+    if (idx >= n_local) return;
+    for (; sub != 0ull; ++m, sub >>= 2) {
+        const unsigned q = (unsigned)(sub & 3ull);
+        if (q != 0u) thread_vecmat(v, tables + ((size_t)m * 3 + (q - 1)) * 160 * kRowWords);
     }
     xs.d[idx] = d;
     xs.v0[idx] = v[0]; xs.v1[idx] = v[1]; xs.v2[idx] = v[2]; xs.v3[idx] = v[3]; xs.v4[idx] = v[4];
