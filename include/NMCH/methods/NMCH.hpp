@@ -49,6 +49,11 @@ public:
     float compute_grid(int n_points, const float *k, const float *theta, const float *sigma, float *strike_price_out,
                        float *price_squared_out, float *err_out);
 
+    /* One compute() pass priced at a strike vector, with the pathwise delta E[1{S_T>K} S_T/S_0] (the reference fixes
+       K = S_0, NMCH.cu:7).  Outputs (each n_strikes long, may be null): E[(S_T-K)^+], E[((S_T-K)^+)^2], delta.
+       Returns the launch time in ms. */
+    float compute_strikes(int n_strikes, const float *strikes, float *price_out, float *price_squared_out, float *delta_out);
+
     virtual ~NMCH();
 
 protected:

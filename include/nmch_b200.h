@@ -89,6 +89,25 @@ int nmch_engine_explore_async(nmch_engine_t *e, void *cuda_stream, const float *
  * returns the terminal S and V of local paths [0, count) into HOST arrays. */
 int nmch_engine_compute_paths(nmch_engine_t *e, float *S_out, float *V_out, unsigned long long count,
                               nmch_moments_t *out);
+/* ---- strike vector + pathwise delta in the same pass (no reference equivalent: it fixes
+ * K = S_0, src/NMCH/methods/NMCH.cu:7).  The paths of ONE compute() pass price n_strikes calls: the path kernel
+ * keeps the terminal prices on the device (4 bytes per path) and a second small kernel folds them per strike with
+ * the same deterministic FP64 reduction.  Streams advance exactly as for compute(). */
+#define NMCH_MAX_STRIKES 64
+typedef struct {
+    float  strike;
+    double sum_payoff;        /* sum (S_T - K)^+                      */
+    double sum_payoff_sq;     /* sum ((S_T - K)^+)^2                  */
+    double sum_delta;         /* sum 1{S_T > K} S_T / S_0   (pathwise d payoff / d S_0) */
+    double sum_itm;           /* sum 1{S_T > K}                       */
+    unsigned long long n_paths;
+    float  exec_ms;
+} nmch_strike_moments_t;
+int nmch_engine_compute_strikes(nmch_engine_t *e, const float *strikes, int n_strikes, nmch_strike_moments_t *out);
+/* stream form: 4*n_strikes raw sums {payoff, payoff^2, delta, itm} per strike into DEVICE memory, no host sync */
+int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const float *strikes, int n_strikes,
+                                      double *d_moments);
+
 /* finalize() (NMCH_FE.cu:326-331); idempotent here (the reference double-frees) */
 int nmch_engine_finalize(nmch_engine_t *e);
 void nmch_engine_destroy(nmch_engine_t *e);
@@ -115,6 +134,7 @@ int nmch_group_explore(nmch_group_t *g, const float *k, const float *theta, cons
                        nmch_moments_t *out);
 int nmch_group_finalize(nmch_group_t *g);
 void nmch_group_destroy(nmch_group_t *g);
+int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_strikes, nmch_strike_moments_t *out);
 float nmch_group_init_ms(const nmch_group_t *g);
 int nmch_group_size(const nmch_group_t *g);
 

@@ -29,6 +29,11 @@ class NmchMoments(C.Structure):
                 ("exec_ms", C.c_float)]
 
 
+class NmchStrikeMoments(C.Structure):
+    _fields_ = [("strike", C.c_float), ("sum_payoff", C.c_double), ("sum_payoff_sq", C.c_double),
+                ("sum_delta", C.c_double), ("sum_itm", C.c_double), ("n_paths", C.c_ulonglong), ("exec_ms", C.c_float)]
+
+
 class NmchLaunchInfo(C.Structure):
     _fields_ = [("grid_x", C.c_int), ("grid_y", C.c_int), ("block_threads", C.c_int),
                 ("paths_per_thread", C.c_int), ("regs_per_thread", C.c_int), ("sm_count", C.c_int),
@@ -38,9 +43,10 @@ class NmchLaunchInfo(C.Structure):
 EXPORTS = [
     "nmch_engine_create", "nmch_engine_init", "nmch_engine_set_params", "nmch_engine_compute",
     "nmch_engine_compute_async", "nmch_engine_explore", "nmch_engine_explore_async",
-    "nmch_engine_compute_paths", "nmch_engine_finalize", "nmch_engine_destroy", "nmch_engine_init_ms",
+    "nmch_engine_compute_paths", "nmch_engine_compute_strikes", "nmch_engine_compute_strikes_async",
+    "nmch_engine_finalize", "nmch_engine_destroy", "nmch_engine_init_ms",
     "nmch_engine_launch_info", "nmch_group_create", "nmch_group_init", "nmch_group_set_params", "nmch_group_compute",
-    "nmch_group_explore", "nmch_group_finalize", "nmch_group_destroy", "nmch_group_init_ms", "nmch_group_size",
+    "nmch_group_explore", "nmch_group_compute_strikes", "nmch_group_finalize", "nmch_group_destroy", "nmch_group_init_ms", "nmch_group_size",
     "nmch_status_string", "nmch_last_error", "nmch_device_count", "nmch_version",
 ]
 
@@ -71,6 +77,9 @@ def load() -> C.CDLL:
     L.nmch_engine_explore.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.POINTER(NmchMoments)]
     L.nmch_engine_explore_async.argtypes = [vp, vp, f32p, f32p, f32p, C.c_int, vp]
     L.nmch_engine_compute_paths.argtypes = [vp, f32p, f32p, C.c_ulonglong, C.POINTER(NmchMoments)]
+    L.nmch_engine_compute_strikes.argtypes = [vp, f32p, C.c_int, C.POINTER(NmchStrikeMoments)]
+    L.nmch_engine_compute_strikes_async.argtypes = [vp, vp, f32p, C.c_int, vp]
+    L.nmch_group_compute_strikes.argtypes = [vp, f32p, C.c_int, C.POINTER(NmchStrikeMoments)]
     L.nmch_engine_finalize.argtypes = [vp]
     L.nmch_engine_destroy.argtypes = [vp]
     L.nmch_engine_destroy.restype = None

@@ -439,6 +439,66 @@ int nmch_engine_compute_paths(nmch_engine_t *e, float *S_out, float *V_out, unsi
     return NMCH_OK;
 }
 
+// shared by the blocking and the stream form: path kernel (keeps S_T on the device) + strike kernel
+static int strikes_launch(nmch_engine *e, cudaStream_t stream, const float *strikes, int n_strikes, double *d_out4)
+{
+    int rc = ensure_sv(e, (size_t)e->n_local);
+    if (rc) return rc;
+    // reduction slots: 0 = the path kernel's own K = S_0 moments, 1 + 2j / 2 + 2j = strike j
+    const size_t slots = 1 + 2 * (size_t)n_strikes;
+    rc = ensure_buffers(e, slots, (size_t)strike_blocks_per_slot(), (size_t)n_strikes * sizeof(float));
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(e->d_points, strikes, (size_t)n_strikes * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaStreamSynchronize(stream));                     // `strikes` is caller memory of unknown lifetime
+    rc = launch_points(e, stream, nullptr, nullptr, nullptr, 1, e->h_out_dev, e->d_S, e->d_V);
+    if (rc) return rc;
+    // same stream: the path kernel (and its use of the partial buffer) is complete before the strike kernel starts
+    ReduceBuffers rb{e->d_partials, e->d_tickets + 1, d_out4};
+    CU_TRY(launch_strike_moments(e->d_S, e->n_local, static_cast<const float *>(e->d_points), n_strikes, e->p.S_0, rb, stream));
+    e->launches += 1;
+    return NMCH_OK;
+}
+
+int nmch_engine_compute_strikes(nmch_engine_t *e, const float *strikes, int n_strikes, nmch_strike_moments_t *out)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!strikes || !out || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return fail(NMCH_ERR_ARG, "bad strike arguments");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    rc = ensure_buffers(e, 1 + 2 * (size_t)n_strikes, 1, 0);   // host-visible result buffer large enough
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = strikes_launch(e, e->stream, strikes, n_strikes, e->h_out_dev + 2);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev1, e->stream));
+    CU_TRY(cudaEventSynchronize(e->ev1));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    for (int j = 0; j < n_strikes; ++j) {
+        const double *m = e->h_out + 2 + 4 * (size_t)j;
+        out[j].strike = strikes[j];
+        out[j].sum_payoff = m[0];
+        out[j].sum_payoff_sq = m[1];
+        out[j].sum_delta = m[2];
+        out[j].sum_itm = m[3];
+        out[j].n_paths = e->n_local;
+        out[j].exec_ms = ms;
+    }
+    return NMCH_OK;
+}
+
+int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const float *strikes, int n_strikes,
+                                      double *d_moments)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!strikes || !d_moments || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return fail(NMCH_ERR_ARG, "bad strike arguments");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    return strikes_launch(e, static_cast<cudaStream_t>(cuda_stream), strikes, n_strikes, d_moments);
+}
+
 int nmch_engine_finalize(nmch_engine_t *e)
 {
     if (!e) return fail(NMCH_ERR_ARG, "null engine");

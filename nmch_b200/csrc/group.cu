@@ -247,6 +247,49 @@ int nmch_group_explore(nmch_group_t *g, const float *k, const float *theta, cons
     return rc;
 }
 
+int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_strikes, nmch_strike_moments_t *out)
+{
+    if (!g || !g->inited) return engine_fail(NMCH_ERR_STATE, "group not initialised");
+    if (!strikes || !out || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return engine_fail(NMCH_ERR_ARG, "bad strike arguments");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = ensure_moments(g, 2 * (size_t)n_strikes);          // 4 doubles per strike
+    if (rc) return rc;
+    for (int i = 0; i < g->n; ++i) {
+        cudaSetDevice(g->dev[i]);
+        cudaEventRecord(g->ev0[i], g->stream[i]);
+        rc = nmch_engine_compute_strikes_async(g->eng[i], g->stream[i], strikes, n_strikes, g->d_mom[i]);
+        if (rc) { cudaSetDevice(prev); return rc; }
+    }
+    if (g->n > 1) {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int i = 0; i < g->n && r == ncclSuccess; ++i)
+            r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], 4 * (size_t)n_strikes, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
+        if (r == ncclSuccess) r = g_nccl.GroupEnd();
+        if (r != ncclSuccess) { cudaSetDevice(prev); return nccl_fail("strike allreduce", r); }
+    }
+    float ms = 0.0f;
+    for (int i = 0; i < g->n; ++i) {
+        cudaSetDevice(g->dev[i]);
+        if (i == 0) cudaMemcpyAsync(g->h_mom, g->d_mom[0], 4 * (size_t)n_strikes * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]);
+        cudaEventRecord(g->ev1[i], g->stream[i]);
+    }
+    for (int i = 0; i < g->n; ++i) {
+        cudaSetDevice(g->dev[i]);
+        cudaError_t err = cudaEventSynchronize(g->ev1[i]);
+        if (err != cudaSuccess) { cudaSetDevice(prev); return engine_fail(NMCH_ERR_CUDA, "group strikes", err); }
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, g->ev0[i], g->ev1[i]);
+        if (t > ms) ms = t;
+    }
+    for (int j = 0; j < n_strikes; ++j) {
+        const double *m = g->h_mom + 4 * (size_t)j;
+        out[j] = nmch_strike_moments_t{strikes[j], m[0], m[1], m[2], m[3], g->n_paths, ms};
+    }
+    cudaSetDevice(prev);
+    return NMCH_OK;
+}
+
 int nmch_group_finalize(nmch_group_t *g)
 {
     if (!g) return engine_fail(NMCH_ERR_ARG, "null group");

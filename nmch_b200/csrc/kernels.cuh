@@ -67,6 +67,11 @@ cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind, in
                              const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out,
                              float *V_out, cudaStream_t stream, KernelInfo *info);
 
+// strike_kernels.cu: per-strike payoff / delta sums from terminal prices kept on the device
+cudaError_t launch_strike_moments(const float *d_S, unsigned long long n_local, const float *d_strikes, int n_strikes,
+                                  float S0, ReduceBuffers rb, cudaStream_t stream);
+int strike_blocks_per_slot();
+
 // xorwow.cu
 struct XorwowSkipTables;                // device tables M_m^q, q = 1..3, m = 0..31
 cudaError_t xorwow_tables_create(XorwowSkipTables **out);

@@ -106,6 +106,15 @@ class Engine:
                                                        count, C.byref(m)))
         return S, V, Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms)
 
+    def compute_strikes(self, strikes):
+        """One compute() pass priced at a vector of strikes, with the pathwise delta."""
+        strikes = np.ascontiguousarray(strikes, np.float32)
+        out = (capi.NmchStrikeMoments * len(strikes))()
+        capi.check(self._lib.nmch_engine_compute_strikes(self._h, strikes.ctypes.data_as(C.POINTER(C.c_float)),
+                                                         len(strikes), out))
+        return [{"strike": m.strike, "moments": Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms),
+                 "delta": m.sum_delta / m.n_paths, "itm": m.sum_itm / m.n_paths} for m in out]
+
     def finalize(self) -> None:
         if self._h:
             capi.check(self._lib.nmch_engine_finalize(self._h))
@@ -173,6 +182,14 @@ class Group:
         capi.check(self._lib.nmch_group_explore(self._h, k.ctypes.data_as(f32p), theta.ctypes.data_as(f32p),
                                                 sigma.ctypes.data_as(f32p), len(k), out))
         return [Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms) for m in out]
+
+    def compute_strikes(self, strikes):
+        strikes = np.ascontiguousarray(strikes, np.float32)
+        out = (capi.NmchStrikeMoments * len(strikes))()
+        capi.check(self._lib.nmch_group_compute_strikes(self._h, strikes.ctypes.data_as(C.POINTER(C.c_float)),
+                                                        len(strikes), out))
+        return [{"strike": m.strike, "moments": Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms),
+                 "delta": m.sum_delta / m.n_paths, "itm": m.sum_itm / m.n_paths} for m in out]
 
     @property
     def size(self) -> int:

@@ -117,6 +117,22 @@ float NMCH<rnd_state>::compute_grid(int n_points, const float *kk, const float *
 }
 
 template <typename rnd_state>
+float NMCH<rnd_state>::compute_strikes(int n_strikes, const float *strikes, float *price_out, float *sq_out, float *delta_out)
+{
+    if (!group) testNMCH(NMCH_ERR_STATE);
+    testNMCH(nmch_group_set_params(group, k, theta, sigma));
+    std::vector<nmch_strike_moments_t> m((size_t)(n_strikes > 0 ? n_strikes : 0));
+    testNMCH(nmch_group_compute_strikes(group, strikes, n_strikes, m.data()));
+    for (int j = 0; j < n_strikes; ++j) {
+        const double n = (double)m[j].n_paths;
+        if (price_out) price_out[j] = (float)(m[j].sum_payoff / n);
+        if (sq_out) sq_out[j] = (float)(m[j].sum_payoff_sq / n);
+        if (delta_out) delta_out[j] = (float)(m[j].sum_delta / n);
+    }
+    return n_strikes > 0 ? m[0].exec_ms : 0.0f;
+}
+
+template <typename rnd_state>
 void NMCH<rnd_state>::engine_finalize()
 {
     if (group) testNMCH(nmch_group_finalize(group));               // idempotent, unlike the reference's double free

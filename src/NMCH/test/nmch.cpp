@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "NMCH/methods/NMCH_EM.hpp"
 #include "NMCH/methods/NMCH_FE.hpp"
@@ -21,7 +22,7 @@ struct Options {
     int NTPB = 512, NB = 512, N = 1000, gpus = 1, ppt = 0;
     float T = 1.0f, S_0 = 1.0f, v_0 = 0.1f, r = 0.0f, k = 0.5f, rho = -0.7, theta = 0.1f, sigma = 0.3f;
     unsigned long long seed = 1234;
-    std::string method = "fe", g = "abs", rng = "philox";
+    std::string method = "fe", g = "abs", rng = "philox", strikes;
     bool json = false;
 };
 
@@ -49,6 +50,7 @@ void usage(const char *argv0)
     printf("  --rng <philox|xorwow|philox-compat>  Stream mode (default: philox)\n");
     printf("  --gpus <int>       GPUs to shard the paths over (default: 1)\n");
     printf("  --paths-per-thread <int>  1, 2, 4 or 8 (default: auto)\n");
+    printf("  --strikes <k1,k2,..>  Also price these strikes (and pathwise deltas) on a second pass of the streams\n");
     printf("  --json             Also print one JSON line with the raw moments\n");
 }
 
@@ -72,6 +74,19 @@ int run(const Options &o)
                o.method.c_str(), o.rng.c_str(), o.g.c_str(), o.gpus, n, o.N, m.get_sum_payoff(), m.get_sum_payoff_sq(),
                m.get_strike_price(), m.get_price_squared(), m.get_std_error(), m.get_err(), m.get_execution_time(),
                o.method == "fe" ? "path_steps_per_s" : "paths_per_s", units / (m.get_execution_time() * 1e-3));
+    }
+    if (!o.strikes.empty()) {
+        std::vector<float> ks;
+        for (size_t p = 0; p < o.strikes.size();) {
+            size_t q = o.strikes.find(',', p);
+            if (q == std::string::npos) q = o.strikes.size();
+            ks.push_back((float)atof(o.strikes.substr(p, q - p).c_str()));
+            p = q + 1;
+        }
+        std::vector<float> pr(ks.size()), sq(ks.size()), dl(ks.size());
+        const float ms = m.compute_strikes((int)ks.size(), ks.data(), pr.data(), sq.data(), dl.data());
+        printf("strike, price, price_squared, delta   (one pass, %f ms)\n", ms);
+        for (size_t j = 0; j < ks.size(); ++j) printf("%f, %f, %f, %f\n", ks[j], pr[j], sq[j], dl[j]);
     }
     m.finalize();
     return 0;
@@ -101,6 +116,7 @@ int main(int argc, char **argv)
         else if (has("--rng")) o.rng = argv[++i];
         else if (has("--gpus")) o.gpus = atoi(argv[++i]);
         else if (has("--paths-per-thread")) o.ppt = atoi(argv[++i]);
+        else if (has("--strikes")) o.strikes = argv[++i];
         else if (strcmp(argv[i], "--json") == 0) o.json = true;
         else if (strcmp(argv[i], "--help") == 0) { usage(argv[0]); return 0; }
     }
