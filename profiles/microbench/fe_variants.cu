@@ -84,6 +84,24 @@ __global__ void __launch_bounds__(THREADS, MINB) fe(const __grid_constant__ Cons
             }
             ++blk;
         }
+    } else if (VARIANT == 3) {
+#pragma unroll 1
+        for (int it = 0; it < c.N / 3; ++it) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10(blk, 0u, path0 + j * THREADS, 0u, c.keys);
+                const uint32_t rA = ((w.x >> 9) & 0x7ffffeu) | 0x3f800000u;
+                const uint32_t aA = (__funnelshift_r(w.y, w.x, 19) & 0x7ffff8u) | 0x3f800000u;
+                const uint32_t rB = ((w.y << 1) & 0x7ffffeu) | 0x3f800000u;
+                const uint32_t aB = ((w.z >> 9) & 0x7ffff8u) | 0x3f800000u;
+                const uint32_t rC = (__funnelshift_r(w.w, w.z, 21) & 0x7ffffeu) | 0x3f800000u;
+                const uint32_t aC = ((w.w << 1) & 0x7ffff8u) | 0x3f800000u;
+                step_f<MODE>(S[j], V[j], __uint_as_float(rA), __uint_as_float(aA), c);
+                step_f<MODE>(S[j], V[j], __uint_as_float(rB), __uint_as_float(aB), c);
+                step_f<MODE>(S[j], V[j], __uint_as_float(rC), __uint_as_float(aC), c);
+            }
+            ++blk;
+        }
     } else {
 #pragma unroll 1
         for (int it = 0; it < c.N / 5; ++it) {
@@ -147,21 +165,13 @@ int main()
     c.S0 = 1.0f; c.v0 = 0.1f; c.K = 1.0f; c.N = 1000;
     double *d_out;
     cudaMalloc(&d_out, 8);
-    run<4, 256, 1, 0, 0>("product loop", c, d_out);
-    run<4, 128, 1, 0, 0>("product loop", c, d_out);
-    run<4, 128, 10, 0, 0>("product loop, minblocks 10 (<=48 regs)", c, d_out);
-    run<4, 128, 12, 0, 0>("product loop, minblocks 12 (<=40 regs)", c, d_out);
-    run<4, 64, 20, 0, 0>("product loop, 64 threads minblocks 20", c, d_out);
-    run<4, 256, 5, 0, 0>("product loop, 256 threads minblocks 5", c, d_out);
-    run<4, 128, 10, 2, 0>("unroll x2, minblocks 10", c, d_out);
-    run<4, 128, 8, 2, 0>("unroll x2, minblocks 8", c, d_out);
-    run<2, 128, 16, 2, 0>("unroll x2, P=2 minblocks 16", c, d_out);
-    run<2, 128, 12, 2, 0>("unroll x2, P=2 minblocks 12", c, d_out);
-    run<2, 128, 12, 0, 0>("product loop, P=2 minblocks 12", c, d_out);
-    run<8, 128, 5, 0, 0>("product loop, P=8 minblocks 5", c, d_out);
-    run<8, 128, 6, 0, 0>("product loop, P=8 minblocks 6", c, d_out);
-    run<4, 128, 10, 0, 1>("(.)+ floor, minblocks 10", c, d_out);
-    run<4, 128, 10, 1, 0>("dense, minblocks 10", c, d_out);
-    run<2, 128, 12, 1, 0>("dense, P=2 minblocks 12", c, d_out);
+    c.N = 999;
+    run<4, 128, 10, 0, 0>("product loop (N=998)", c, d_out);
+    run<4, 128, 10, 3, 0>("3 steps per block (22/20-bit fields), minb 10", c, d_out);
+    run<4, 128, 8, 3, 0>("3 steps per block, minb 8", c, d_out);
+    run<4, 256, 5, 3, 0>("3 steps per block, 256 thr minb 5", c, d_out);
+    run<2, 128, 12, 3, 0>("3 steps per block, P=2 minb 12", c, d_out);
+    run<8, 128, 6, 3, 0>("3 steps per block, P=8 minb 6", c, d_out);
+    run<4, 128, 10, 3, 1>("3 steps per block, (.)+ floor", c, d_out);
     return 0;
 }
