@@ -1,0 +1,91 @@
+"""Pins against tests/golden/ref_cuda_b200.json: outputs of the UNMODIFIED reference CUDA build run on a B200
+(generator: tests/golden/make_ref_cuda_golden.py).  CPU part: the oracle reproduces the reference's numbers;
+GPU part: so do the compat stream modes of the engine, through the C ABI, to the north-star tolerance (1e-5)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cuda_b200.json")))
+PKEYS = ("T", "S_0", "v_0", "r", "k", "rho", "theta", "sigma")
+
+
+def _params(flags):
+    return o.Params(N=flags["N"], **{k: flags[k] for k in PKEYS if k in flags})
+
+
+def _rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["flags"]["method"] == "fe"],
+                         ids=lambda c: "{rng}-{NTPB}x{NB}-N{N}".format(**c["flags"]))
+def test_oracle_fe_reproduces_reference_cuda(case):
+    f = case["flags"]
+    n = f["NTPB"] * f["NB"]
+    rng = o.RNG_XORWOW if f["rng"] == "xorwow" else o.RNG_PHILOX
+    for call, want in enumerate(case["calls"], start=1):
+        got = o.fe_run(_params(f), rng=rng, n_paths=n, calls=call)
+        # host libm vs device __sincosf/logf: per-path 1e-6, averaged out; the reference's float atomics add ~3e-7
+        assert _rel(got["mean"], want["E"]) < 1e-5, (call, got["mean"], want["E"])
+        var_ref = want["E2"] - want["E"] ** 2
+        assert _rel(got["mean_sq"] - got["mean"] ** 2, var_ref) < 1e-5 + 4 * want["E2_spread"] / var_ref
+
+
+def test_oracle_fe_sweep_reproduces_reference_cuda():
+    sw = GOLD["sweeps"][0]
+    assert sw["flags"]["method"] == "fe"
+    k, th, sg = (np.array(x, np.float32) for x in zip(*sw["points"]))
+    n = sw["flags"]["NTPB"] * sw["flags"]["NB"]
+    sums = o.fe_sweep(o.Params(N=sw["flags"]["N"]), k, th, sg, rng=o.RNG_XORWOW, n_paths=n)
+    for i, want in enumerate(sw["calls"]):
+        assert _rel(sums[i, 0] / n, want["E"]) < 2e-5, (i, sums[i, 0] / n, want["E"])
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["flags"]["method"] == "em"],
+                         ids=lambda c: "{rng}-{NTPB}x{NB}-N{N}".format(**c["flags"]))
+def test_oracle_em_tracks_reference_cuda(case):
+    f = case["flags"]
+    n = f["NTPB"] * f["NB"]
+    if n * f["N"] > 4e7:
+        pytest.skip("large EM case: covered on the GPU")
+    rng = o.RNG_XORWOW if f["rng"] == "xorwow" else o.RNG_PHILOX
+    got = o.em_run(_params(f), rng=rng, n_paths=n)
+    want = case["calls"][0]
+    se = o.std_error(got["mean"], got["mean_sq"], n)
+    # host branches of cuRAND's Poisson helpers differ from the device's approximations: a flipped accept/reject
+    # re-routes a path, so agreement is statistical (well inside one standard error), not digit for digit
+    assert abs(got["mean"] - want["E"]) < 0.5 * se + 1e-6, (got["mean"], want["E"], se)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: "{method}-{rng}-{NTPB}x{NB}-N{N}".format(**c["flags"]))
+def test_engine_compat_reproduces_reference_cuda(case):
+    from nmch_b200 import engine as E
+    f = case["flags"]
+    kw = {k: f[k] for k in PKEYS if k in f}
+    with E.Engine(NTPB=f["NTPB"], NB=f["NB"], N=f["N"], method=E.METHOD_FE if f["method"] == "fe" else E.METHOD_EM,
+                  rng=E.RNG_XORWOW_COMPAT if f["rng"] == "xorwow" else E.RNG_PHILOX_COMPAT, **kw) as e:
+        e.init(1234)
+        for want in case["calls"]:
+            m = e.compute()
+            var_ref = want["E2"] - want["E"] ** 2
+            assert _rel(m.mean, want["E"]) < 1e-5 + 4 * want["E_spread"] / want["E"], (m.mean, want)
+            assert _rel(m.variance, var_ref) < 1e-5 + 4 * want["E2_spread"] / var_ref, (m.variance, var_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sw", GOLD["sweeps"], ids=lambda s: s["flags"]["method"])
+def test_engine_compat_sweep_reproduces_reference_cuda(sw):
+    from nmch_b200 import engine as E
+    f = sw["flags"]
+    k, th, sg = (np.array(x, np.float32) for x in zip(*sw["points"]))
+    with E.Engine(NTPB=f["NTPB"], NB=f["NB"], N=f["N"], method=E.METHOD_FE if f["method"] == "fe" else E.METHOD_EM,
+                  rng=E.RNG_XORWOW_COMPAT) as e:
+        e.init(1234)
+        got = e.explore(k, th, sg)                      # one launch == the reference's sequential set_* + compute()
+    for m, want in zip(got, sw["calls"]):
+        assert _rel(m.mean, want["E"]) < 2e-5, (m.mean, want["E"])
