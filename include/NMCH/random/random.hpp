@@ -8,7 +8,7 @@
 //
 //   curandStateXORWOW_t        -> cuRAND-XORWOW-compatible stream (draw-for-draw validation mode)
 //   curandStatePhilox4_32_10_t -> native counter-based Philox4x32-10 (the product path)
-//   curandStateMRG32k3a_t      -> not on the hot path; accepted as an alias of the native mode (note on stderr)
+//   curandStateMRG32k3a_t      -> cuRAND-MRG32k3a-compatible stream (validation mode, like XORWOW)
 #ifndef NMCH_RANDOM_HPP
 #define NMCH_RANDOM_HPP
 
@@ -21,12 +21,12 @@ typedef struct curandStatePhilox4_32_10 curandStatePhilox4_32_10_t;
 
 namespace nmch::random {
 
-enum class stream_mode { native_philox, xorwow_compat, philox_compat };
+enum class stream_mode { native_philox, xorwow_compat, philox_compat, mrg32k3a_compat };
 
 template <typename rnd_state> struct tag_traits;
 template <> struct tag_traits<curandStateXORWOW_t> { static constexpr stream_mode mode = stream_mode::xorwow_compat; static constexpr bool alias = false; };
 template <> struct tag_traits<curandStatePhilox4_32_10_t> { static constexpr stream_mode mode = stream_mode::native_philox; static constexpr bool alias = false; };
-template <> struct tag_traits<curandStateMRG32k3a_t> { static constexpr stream_mode mode = stream_mode::native_philox; static constexpr bool alias = true; };
+template <> struct tag_traits<curandStateMRG32k3a_t> { static constexpr stream_mode mode = stream_mode::mrg32k3a_compat; static constexpr bool alias = false; };
 
 }  // namespace nmch::random
 

@@ -38,8 +38,10 @@ typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
  *                  Philox instantiation; floats agree to ~2^-23 per draw)
  *   XORWOW_COMPAT  curandStateXORWOW_t-compatible: same integer stream, same IEEE transforms and FMA
  *                  contraction as the reference's CUDA build
- *   PHILOX_COMPAT  curandStatePhilox4_32_10_t-compatible (reference CLI default, nmch.cu:119,130) */
-typedef enum { NMCH_RNG_PHILOX = 0, NMCH_RNG_XORWOW_COMPAT = 1, NMCH_RNG_PHILOX_COMPAT = 2 } nmch_rng;
+ *   PHILOX_COMPAT  curandStatePhilox4_32_10_t-compatible (reference CLI default, nmch.cu:119,130)
+ *   MRG32K3A_COMPAT curandStateMRG32k3a_t-compatible (the third tag the reference instantiates, NMCH.cu:31) */
+typedef enum { NMCH_RNG_PHILOX = 0, NMCH_RNG_XORWOW_COMPAT = 1, NMCH_RNG_PHILOX_COMPAT = 2,
+               NMCH_RNG_MRG32K3A_COMPAT = 3 } nmch_rng;
 
 /* Replaces the constructor arguments of nmch::methods::NMCH (include/NMCH/methods/NMCH.hpp:42,
  * src/NMCH/methods/NMCH.cu:6-10).  Zero in an "auto" field selects the default. */

@@ -18,6 +18,7 @@
 
 #include <vector>
 
+#include "compat_math.cuh"
 #include "engine_internal.cuh"
 
 namespace nmchb {
@@ -303,14 +304,16 @@ em_compat_xorwow_kernel(const __grid_constant__ EmCompatLaunch L, const RawPoint
     }
 }
 
+// cuRAND-layout states kept as an array of structures (Philox: 64 B, MRG32k3a: 48 B per path)
+template <typename State>
 __global__ void __launch_bounds__(256)
-em_compat_philox_kernel(const __grid_constant__ EmCompatLaunch L, const RawPoint *__restrict__ pts,
-                        curandStatePhilox4_32_10_t *__restrict__ states, ReduceBuffers rb,
-                        float *__restrict__ S_out, float *__restrict__ V_out)
+em_compat_state_kernel(const __grid_constant__ EmCompatLaunch L, const RawPoint *__restrict__ pts,
+                       State *__restrict__ states, ReduceBuffers rb,
+                       float *__restrict__ S_out, float *__restrict__ V_out)
 {
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
-    curandStatePhilox4_32_10_t st;
+    State st;
     if (valid) st = states[idx];
     for (int point = 0; point < L.n_points; ++point) {
         const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
@@ -329,12 +332,65 @@ em_compat_philox_kernel(const __grid_constant__ EmCompatLaunch L, const RawPoint
     if (valid) states[idx] = st;
 }
 
-// cuRAND Philox state for the compat path: counter = (0, 0, path, 0), key = seed (curand_kernel.h:1022-1037)
-__global__ void em_philox_state_init_kernel(curandStatePhilox4_32_10_t *states, unsigned long long seed,
-                                            unsigned long long first_path, unsigned long long n_local)
+// cuRAND state per path, subsequence = global path index (reference: src/NMCH/random/random.cu:6-10).
+// Philox: counter = (0, 0, path, 0), key = seed (curand_kernel.h:1022-1037); MRG32k3a: seed scramble + 3x3
+// matrix-power skip of 2^76 draws per subsequence (curand_kernel.h:1274-1300).
+template <typename State>
+__global__ void curand_state_init_kernel(State *states, unsigned long long seed,
+                                         unsigned long long first_path, unsigned long long n_local)
 {
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n_local) curand_init(seed, first_path + idx, 0, &states[idx]);
+}
+
+// FE for the MRG32k3a tag (the XORWOW / Philox tags have their own stream code in fe_kernels.cu): cuRAND's
+// curand_normal2 on the MRG state (curand_normal.h:89-108, 466-469) + the reference's pinned update.
+template <int FLOOR>
+__global__ void __launch_bounds__(256)
+fe_compat_mrg_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict__ pts,
+                     curandStateMRG32k3a_t *__restrict__ states, ReduceBuffers rb, float *__restrict__ S_out,
+                     float *__restrict__ V_out)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < L.n_local;
+    curandStateMRG32k3a_t st;
+    if (valid) st = states[idx];
+    for (int point = 0; point < L.n_points; ++point) {
+        const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
+        float S = L.S0, V = L.v0;
+        if (valid) {
+            for (int n = 0; n < L.N; ++n) {
+                const float2 g = curand_normal2(&st);
+                fe_step_compat<FLOOR>(S, V, g.x, g.y, L.r, rp.k, L.rho, rp.theta, rp.sigma, L.dt, L.sqrt_dt, L.sqrt_rho);
+            }
+        }
+        double pay = 0.0;
+        if (valid) {
+            pay = (double)fmaxf(0.0f, S - L.K);
+            if (S_out != nullptr && point == L.n_points - 1) {
+                S_out[idx] = S;
+                V_out[idx] = V;
+            }
+        }
+        block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+    }
+    if (valid) states[idx] = st;
+}
+
+cudaError_t launch_fe_compat_mrg(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, void *states,
+                                 ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
+{
+    auto *st = static_cast<curandStateMRG32k3a_t *>(states);
+    cudaFuncAttributes attr{};
+    if (floor_kind == kFloorAbs) {
+        fe_compat_mrg_kernel<kFloorAbs><<<(unsigned)L.blocks_per_point, 256, 0, stream>>>(L, d_pts, st, rb, S_out, V_out);
+        cudaFuncGetAttributes(&attr, fe_compat_mrg_kernel<kFloorAbs>);
+    } else {
+        fe_compat_mrg_kernel<kFloorPlus><<<(unsigned)L.blocks_per_point, 256, 0, stream>>>(L, d_pts, st, rb, S_out, V_out);
+        cudaFuncGetAttributes(&attr, fe_compat_mrg_kernel<kFloorPlus>);
+    }
+    if (info) *info = KernelInfo{L.blocks_per_point, 1, 256, 1, attr.numRegs};
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -369,24 +425,28 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
 }
 
 
-int em_philox_compat_init(nmch_engine *e)
+template <typename State>
+static int curand_states_init(nmch_engine *e)
 {
     const size_t n = (size_t)e->n_local;
-    cudaError_t err = cudaMalloc(&e->em_philox_states, n * sizeof(curandStatePhilox4_32_10_t));
-    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "cudaMalloc(philox states)", err);
+    cudaError_t err = cudaMalloc(&e->curand_states, n * sizeof(State));
+    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "cudaMalloc(cuRAND-layout states)", err);
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    em_philox_state_init_kernel<<<blocks, 256, 0, e->stream>>>(
-        static_cast<curandStatePhilox4_32_10_t *>(e->em_philox_states), e->seed, e->first_path, e->n_local);
+    curand_state_init_kernel<State><<<blocks, 256, 0, e->stream>>>(static_cast<State *>(e->curand_states), e->seed,
+                                                                   e->first_path, e->n_local);
     err = cudaGetLastError();
-    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_philox_state_init_kernel", err);
+    if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "curand_state_init_kernel", err);
     e->launches += 1;
     return NMCH_OK;
 }
 
+int em_philox_compat_init(nmch_engine *e) { return curand_states_init<curandStatePhilox4_32_10_t>(e); }
+int mrg_compat_init(nmch_engine *e) { return curand_states_init<curandStateMRG32k3a_t>(e); }
+
 void em_release(nmch_engine *e)
 {
-    if (e->em_philox_states) cudaFree(e->em_philox_states);
-    e->em_philox_states = nullptr;
+    if (e->curand_states) cudaFree(e->curand_states);
+    e->curand_states = nullptr;
 }
 
 int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
@@ -472,10 +532,14 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
     if (p.rng == NMCH_RNG_XORWOW_COMPAT) {
         em_compat_xorwow_kernel<<<(unsigned)bpp, 256, 0, stream>>>(L, d_pts, e->xs, rb, S_out, V_out);
         cudaFuncGetAttributes(&attr, em_compat_xorwow_kernel);
+    } else if (p.rng == NMCH_RNG_PHILOX_COMPAT) {
+        em_compat_state_kernel<curandStatePhilox4_32_10_t><<<(unsigned)bpp, 256, 0, stream>>>(
+            L, d_pts, static_cast<curandStatePhilox4_32_10_t *>(e->curand_states), rb, S_out, V_out);
+        cudaFuncGetAttributes(&attr, em_compat_state_kernel<curandStatePhilox4_32_10_t>);
     } else {
-        em_compat_philox_kernel<<<(unsigned)bpp, 256, 0, stream>>>(
-            L, d_pts, static_cast<curandStatePhilox4_32_10_t *>(e->em_philox_states), rb, S_out, V_out);
-        cudaFuncGetAttributes(&attr, em_compat_philox_kernel);
+        em_compat_state_kernel<curandStateMRG32k3a_t><<<(unsigned)bpp, 256, 0, stream>>>(
+            L, d_pts, static_cast<curandStateMRG32k3a_t *>(e->curand_states), rb, S_out, V_out);
+        cudaFuncGetAttributes(&attr, em_compat_state_kernel<curandStateMRG32k3a_t>);
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_compat_kernel", err);

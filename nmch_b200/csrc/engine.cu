@@ -214,7 +214,10 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                 d_pts = static_cast<const RawPoint *>(e->d_points);
             }
             ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
-            CU_TRY(launch_fe_compat(L, p.rng, p.floor, 256, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
+            if (p.rng == NMCH_RNG_MRG32K3A_COMPAT)
+                CU_TRY(launch_fe_compat_mrg(L, p.floor, d_pts, e->curand_states, rb, S_out, V_out, stream, &e->kinfo));
+            else
+                CU_TRY(launch_fe_compat(L, p.rng, p.floor, 256, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
         }
         e->draw_offset += 2ull * (unsigned long long)p.N * (unsigned long long)n_points;
     } else {
@@ -261,7 +264,7 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (p.N <= 0) return fail(NMCH_ERR_ARG, "N must be positive");
     if (p.method != NMCH_METHOD_FE && p.method != NMCH_METHOD_EM) return fail(NMCH_ERR_ARG, "unknown method");
     if (p.floor != NMCH_FLOOR_ABS && p.floor != NMCH_FLOOR_PLUS) return fail(NMCH_ERR_ARG, "unknown floor");
-    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_PHILOX_COMPAT) return fail(NMCH_ERR_ARG, "unknown rng mode");
+    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_MRG32K3A_COMPAT) return fail(NMCH_ERR_ARG, "unknown rng mode");
     unsigned long long n = p.n_paths;
     if (n == 0) {
         if (p.NTPB <= 0 || p.NB <= 0) return fail(NMCH_ERR_ARG, "NTPB and NB must be positive");
@@ -327,6 +330,9 @@ int nmch_engine_init(nmch_engine_t *e, unsigned long long seed)
         e->launches += 1;
     } else if (e->p.rng == NMCH_RNG_PHILOX_COMPAT && e->p.method == NMCH_METHOD_EM) {
         int rc = em_philox_compat_init(e);
+        if (rc) return rc;
+    } else if (e->p.rng == NMCH_RNG_MRG32K3A_COMPAT) {
+        int rc = mrg_compat_init(e);
         if (rc) return rc;
     }
     int rc = ensure_buffers(e, 1, 1, 0);

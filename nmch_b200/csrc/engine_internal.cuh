@@ -32,7 +32,7 @@ struct nmch_engine {
     // XORWOW-compat state
     nmchb::XorwowSkipTables *xtab = nullptr;
     nmchb::XorwowState xs{};
-    void *em_philox_states = nullptr;        // curandStatePhilox4_32_10_t[n_local], EM Philox-compat only
+    void *curand_states = nullptr;           // cuRAND-layout states (AoS): Philox-compat EM, MRG32k3a-compat FE/EM
     nmchb::KernelInfo kinfo{};
     unsigned long long launches = 0;
 };
@@ -46,6 +46,9 @@ int engine_ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_poi
 int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
                      int n_points, double *d_out, float *S_out, float *V_out);
 int em_philox_compat_init(nmch_engine *e);
+int mrg_compat_init(nmch_engine *e);
+cudaError_t launch_fe_compat_mrg(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, void *states,
+                                 ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 void em_release(nmch_engine *e);
 
 }  // namespace nmchb

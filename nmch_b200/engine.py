@@ -12,8 +12,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import capi
-from .capi import (FLOOR_ABS, FLOOR_PLUS, METHOD_EM, METHOD_FE, RNG_PHILOX, RNG_PHILOX_COMPAT,  # noqa: F401
-                   RNG_XORWOW_COMPAT)
+from .capi import (FLOOR_ABS, FLOOR_PLUS, METHOD_EM, METHOD_FE, RNG_MRG32K3A_COMPAT, RNG_PHILOX,  # noqa: F401
+                   RNG_PHILOX_COMPAT, RNG_XORWOW_COMPAT)
 
 
 @dataclass

@@ -52,7 +52,7 @@ class NMCH:
         elif rnd_state == PHILOX:
             rng = _eng.RNG_PHILOX_COMPAT if compat else _eng.RNG_PHILOX
         elif rnd_state == MRG32K3A:
-            raise NotImplementedError("curandStateMRG32k3a_t is not on the hot path (SURVEY.md §8b): unsupported")
+            rng = _eng.RNG_MRG32K3A_COMPAT
         else:
             raise ValueError(f"unknown rnd_state tag {rnd_state!r}")
         self._engine = _eng.Engine(NTPB, NB, T, S_0, v_0, r, k, rho, theta, sigma, N, method=self._method,

@@ -39,11 +39,23 @@ void crh_u32(int kind, unsigned long long seed, unsigned long long subseq, unsig
         curandStateXORWOW_t s;
         curand_init(seed, subseq, offset, &s);
         for (int i = 0; i < n; ++i) out[i] = curand(&s);
-    } else {
+    } else if (kind == 1) {
         curandStatePhilox4_32_10_t s;
         curand_init(seed, subseq, offset, &s);
         for (int i = 0; i < n; ++i) out[i] = curand(&s);
+    } else {
+        curandStateMRG32k3a_t s;
+        curand_init(seed, subseq, offset, &s);
+        for (int i = 0; i < n; ++i) out[i] = curand(&s);
     }
+}
+
+/* raw MRG32k3a state after curand_init */
+void crh_mrg_init(unsigned long long seed, unsigned long long subseq, unsigned long long offset, uint32_t st[6])
+{
+    curandStateMRG32k3a_t s;
+    curand_init(seed, subseq, offset, &s);
+    for (int i = 0; i < 3; ++i) { st[i] = s.s1[i]; st[3 + i] = s.s2[i]; }
 }
 
 /* XORWOW raw state after n curand_normal2 calls (pins skip + stream position) */
@@ -64,8 +76,12 @@ void crh_normal2(int kind, unsigned long long seed, unsigned long long subseq, i
         curandStateXORWOW_t s;
         curand_init(seed, subseq, 0, &s);
         for (int i = 0; i < n; ++i) { float2 g = curand_normal2(&s); out[2 * i] = g.x; out[2 * i + 1] = g.y; }
-    } else {
+    } else if (kind == 1) {
         curandStatePhilox4_32_10_t s;
+        curand_init(seed, subseq, 0, &s);
+        for (int i = 0; i < n; ++i) { float2 g = curand_normal2(&s); out[2 * i] = g.x; out[2 * i + 1] = g.y; }
+    } else {
+        curandStateMRG32k3a_t s;
         curand_init(seed, subseq, 0, &s);
         for (int i = 0; i < n; ++i) { float2 g = curand_normal2(&s); out[2 * i] = g.x; out[2 * i + 1] = g.y; }
     }
@@ -82,8 +98,9 @@ static void poisson_t(unsigned long long seed, unsigned long long subseq, double
 }
 extern "C" void crh_poisson(int kind, unsigned long long seed, unsigned long long subseq, double lambda, int n, unsigned *out)
 {
-    if (kind == 0) poisson_t<curandStateXORWOW_t>(seed, subseq, lambda, n, out);
-    else           poisson_t<curandStatePhilox4_32_10_t>(seed, subseq, lambda, n, out);
+    if (kind == 0)      poisson_t<curandStateXORWOW_t>(seed, subseq, lambda, n, out);
+    else if (kind == 1) poisson_t<curandStatePhilox4_32_10_t>(seed, subseq, lambda, n, out);
+    else                poisson_t<curandStateMRG32k3a_t>(seed, subseq, lambda, n, out);
 }
 
 /* mixed sequence exercising the caches: uniform, normal, normal_double, normal, uniform ... */
@@ -104,6 +121,7 @@ static void mixed_t(unsigned long long seed, unsigned long long subseq, int n, d
 }
 extern "C" void crh_mixed(int kind, unsigned long long seed, unsigned long long subseq, int n, double *out)
 {
-    if (kind == 0) mixed_t<curandStateXORWOW_t>(seed, subseq, n, out);
-    else           mixed_t<curandStatePhilox4_32_10_t>(seed, subseq, n, out);
+    if (kind == 0)      mixed_t<curandStateXORWOW_t>(seed, subseq, n, out);
+    else if (kind == 1) mixed_t<curandStatePhilox4_32_10_t>(seed, subseq, n, out);
+    else                mixed_t<curandStateMRG32k3a_t>(seed, subseq, n, out);
 }

@@ -152,6 +152,87 @@ static inline uint32_t xorwow_next(orc_rng_t *s)
 }
 
 /* ======================================================================== */
+/* MRG32k3a  (L'Ecuyer 1999; cuRAND curand_kernel.h:1061-1150 generator,       */
+/* :1274-1300 init, :1181-1225 skip-ahead by 3x3 matrix powers mod m)          */
+/* ======================================================================== */
+#define MRG_M1 4294967087ull
+#define MRG_M2 4294944443ull
+typedef struct { uint64_t a[3][3]; } mat3_t;
+
+static void mat3_mul(const mat3_t *A, const mat3_t *B, uint64_t m, mat3_t *out)
+{
+    mat3_t t;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            unsigned __int128 acc = 0;
+            for (int k = 0; k < 3; ++k) acc += (unsigned __int128)A->a[i][k] * B->a[k][j];
+            t.a[i][j] = (uint64_t)(acc % m);
+        }
+    *out = t;
+}
+
+static void mat3_pow(const mat3_t *A, uint64_t e, uint64_t m, mat3_t *out)
+{
+    mat3_t r = {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}, b = *A;
+    while (e) {
+        if (e & 1ull) mat3_mul(&b, &r, m, &r);
+        mat3_mul(&b, &b, m, &b);
+        e >>= 1;
+    }
+    *out = r;
+}
+
+static void mat3_apply(const mat3_t *A, uint32_t v[3], uint64_t m)
+{
+    uint64_t t[3];
+    for (int k = 0; k < 3; ++k) {
+        unsigned __int128 acc = 0;
+        for (int j = 0; j < 3; ++j) acc += (unsigned __int128)A->a[k][j] * v[j];
+        t[k] = (uint64_t)(acc % m);
+    }
+    for (int k = 0; k < 3; ++k) v[k] = (uint32_t)t[k];
+}
+
+static const mat3_t MRG_A1 = {{{0, 1, 0}, {0, 0, 1}, {MRG_M1 - 810728ull, 1403580ull, 0}}};
+static const mat3_t MRG_A2 = {{{0, 1, 0}, {0, 0, 1}, {MRG_M2 - 1370589ull, 0, 527612ull}}};
+
+static void mrg_skip(orc_rng_t *s, int log2_stride, uint64_t n)
+{   /* advance by n * 2^log2_stride draws: (A^(2^log2_stride))^n */
+    mat3_t b1 = MRG_A1, b2 = MRG_A2, p;
+    for (int i = 0; i < log2_stride; ++i) { mat3_mul(&b1, &b1, MRG_M1, &b1); mat3_mul(&b2, &b2, MRG_M2, &b2); }
+    mat3_pow(&b1, n, MRG_M1, &p); mat3_apply(&p, s->s1, MRG_M1);
+    mat3_pow(&b2, n, MRG_M2, &p); mat3_apply(&p, s->s2, MRG_M2);
+}
+
+static void mrg_init(orc_rng_t *s, uint64_t seed, uint64_t subsequence, uint64_t offset)
+{
+    for (int i = 0; i < 3; ++i) { s->s1[i] = 12345u; s->s2[i] = 12345u; }
+    if (seed != 0ull) {                                       /* curand_kernel.h:1284-1293 */
+        const uint64_t x1 = (uint32_t)seed ^ 0x55555555u;
+        const uint64_t x2 = (uint32_t)((seed >> 32) ^ 0xAAAAAAAAu);
+        s->s1[0] = (uint32_t)((x1 * s->s1[0]) % MRG_M1);
+        s->s1[1] = (uint32_t)((x2 * s->s1[1]) % MRG_M1);
+        s->s1[2] = (uint32_t)((x1 * s->s1[2]) % MRG_M1);
+        s->s2[0] = (uint32_t)((x2 * s->s2[0]) % MRG_M2);
+        s->s2[1] = (uint32_t)((x1 * s->s2[1]) % MRG_M2);
+        s->s2[2] = (uint32_t)((x2 * s->s2[2]) % MRG_M2);
+    }
+    if (subsequence) mrg_skip(s, 76, subsequence);            /* subsequences are 2^76 draws apart */
+    if (offset) mrg_skip(s, 0, offset);
+}
+
+static inline double mrg_next(orc_rng_t *s)
+{   /* one draw in [1, m1]: p1 - p2 (+ m1 if <= 0) */
+    const int64_t p1 = (int64_t)((1403580ull * s->s1[1] + 810728ull * (MRG_M1 - s->s1[0])) % MRG_M1);
+    s->s1[0] = s->s1[1]; s->s1[1] = s->s1[2]; s->s1[2] = (uint32_t)p1;
+    const int64_t p2 = (int64_t)((527612ull * s->s2[2] + 1370589ull * (MRG_M2 - s->s2[0])) % MRG_M2);
+    s->s2[0] = s->s2[1]; s->s2[1] = s->s2[2]; s->s2[2] = (uint32_t)p2;
+    return (p1 <= p2) ? (double)(p1 - p2 + (int64_t)MRG_M1) : (double)(p1 - p2);
+}
+#define MRG_NORM 2.3283065498378288e-10
+#define MRG_BITS_NORM 1.000000048662
+
+/* ======================================================================== */
 /* generic stream front-end                                                  */
 /* ======================================================================== */
 static void philox_incr(uint32_t c[4], uint64_t n)
@@ -171,6 +252,8 @@ void orc_rng_init(orc_rng_t *s, int kind, uint64_t seed, uint64_t subsequence, u
     s->kind = kind;
     if (kind == ORC_RNG_XORWOW) {
         xorwow_init(s, seed, subsequence, offset);
+    } else if (kind == ORC_RNG_MRG32K3A) {
+        mrg_init(s, seed, subsequence, offset);
     } else {
         /* curand_init for Philox, curand_kernel.h:1022-1037, skipahead :971-981 */
         s->key[0] = (uint32_t)seed;
@@ -186,6 +269,7 @@ void orc_rng_init(orc_rng_t *s, int kind, uint64_t seed, uint64_t subsequence, u
 uint32_t orc_rng_next(orc_rng_t *s)
 {
     if (s->kind == ORC_RNG_XORWOW) return xorwow_next(s);
+    if (s->kind == ORC_RNG_MRG32K3A) return (uint32_t)(mrg_next(s) * MRG_BITS_NORM);    /* curand_kernel.h:1161-1167 */
     /* curand(), curand_kernel.h:888-912 */
     uint32_t r = s->out[s->pos++];
     if (s->pos == 4) {
@@ -208,7 +292,11 @@ static inline float uniform_from_u32(uint32_t x)
     return fmaf((float)x, TWO_POW32_INV, TWO_POW32_INV / 2.0f);
 }
 
-float orc_uniform(orc_rng_t *s) { return uniform_from_u32(orc_rng_next(s)); }
+float orc_uniform(orc_rng_t *s)
+{
+    if (s->kind == ORC_RNG_MRG32K3A) return (float)(mrg_next(s) * MRG_NORM);             /* curand_uniform.h:177-180 */
+    return uniform_from_u32(orc_rng_next(s));
+}
 
 static inline void box_muller(uint32_t x, uint32_t y, float *gx, float *gy)
 {   /* _curand_box_muller, curand_normal.h:70-87 : .x pairs with sin */
@@ -221,6 +309,14 @@ static inline void box_muller(uint32_t x, uint32_t y, float *gx, float *gy)
 
 void orc_normal2(orc_rng_t *s, float *gx, float *gy)
 {   /* curand_normal2, curand_normal.h:405-408, 424-427 */
+    if (s->kind == ORC_RNG_MRG32K3A) {                       /* curand_box_muller_mrg, curand_normal.h:89-108 */
+        const float x = orc_uniform(s);
+        const float y = orc_uniform(s) * 6.2831855f;
+        const float r = sqrtf(-2.0f * logf(x));
+        *gx = sinf(y) * r;
+        *gy = cosf(y) * r;
+        return;
+    }
     uint32_t x = orc_rng_next(s);
     uint32_t y = orc_rng_next(s);
     box_muller(x, y, gx, gy);
@@ -242,6 +338,14 @@ float orc_normal(orc_rng_t *s)
 double orc_normal_double(orc_rng_t *s)
 {   /* curand_normal_double, curand_normal.h:581-596 / 615-627 ;
        _curand_box_muller_double :110-133 (host branch: sin/cos(v*pi)) */
+    if (s->bm_flag_d != 1 && s->kind == ORC_RNG_MRG32K3A) {  /* curand_box_muller_mrg_double, curand_normal.h:135-155 */
+        const double x = mrg_next(s) * MRG_NORM;
+        const double y = mrg_next(s) * MRG_NORM * 2.0;
+        const double r = sqrt(-2.0 * log(x));
+        s->bm_extra_d = cos(y * 3.1415926535897932) * r;
+        s->bm_flag_d = 1;
+        return sin(y * 3.1415926535897932) * r;
+    }
     if (s->bm_flag_d != 1) {
         uint32_t x0 = orc_rng_next(s), x1 = orc_rng_next(s);
         uint32_t y0 = orc_rng_next(s), y1 = orc_rng_next(s);

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 /* RNG stream kinds */
-enum { ORC_RNG_XORWOW = 0, ORC_RNG_PHILOX = 1 };
+enum { ORC_RNG_XORWOW = 0, ORC_RNG_PHILOX = 1, ORC_RNG_MRG32K3A = 2 };
 /* variance floor g(.) : README.md:37-40 ; only abs is coded in the reference */
 enum { ORC_FLOOR_ABS = 0, ORC_FLOOR_PLUS = 1 };
 
@@ -45,6 +45,8 @@ typedef struct {
     /* philox */
     uint32_t ctr[4], key[2], out[4];
     int      pos;
+    /* mrg32k3a (curand_kernel.h:208-215) */
+    uint32_t s1[3], s2[3];
     /* Box-Muller caches (curand_normal.h:313-326, 581-596) */
     int      bm_flag;
     float    bm_extra;

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 CURAND_HOST_PATH = os.path.join(HERE, "_ref", "libcurand_host.so")
 REF_HARNESS_PATH = os.path.join(HERE, "_ref", "nmch_ref_harness")
 
-RNG_XORWOW, RNG_PHILOX = 0, 1
+RNG_XORWOW, RNG_PHILOX, RNG_MRG32K3A = 0, 1, 2
 FLOOR_ABS, FLOOR_PLUS = 0, 1
 
 
@@ -30,6 +30,7 @@ class OrcRng(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("d", C.c_uint32), ("v", C.c_uint32 * 5),
         ("ctr", C.c_uint32 * 4), ("key", C.c_uint32 * 2), ("out", C.c_uint32 * 4), ("pos", C.c_int),
+        ("s1", C.c_uint32 * 3), ("s2", C.c_uint32 * 3),
         ("bm_flag", C.c_int), ("bm_extra", C.c_float), ("bm_flag_d", C.c_int), ("bm_extra_d", C.c_double),
     ]
 
@@ -150,6 +151,10 @@ class Rng:
     @property
     def xorwow_state(self):
         return self.s.d, list(self.s.v)
+
+    @property
+    def mrg_state(self):
+        return list(self.s.s1) + list(self.s.s2)
 
 
 def _run(fn, p: Params, args_mid, first_path, n_paths, calls, want_paths, threads):

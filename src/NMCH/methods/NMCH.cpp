@@ -55,8 +55,6 @@ template <typename rnd_state>
 void NMCH<rnd_state>::engine_init(int method, unsigned long long seed, float *tim_init)
 {
     using traits = nmch::random::tag_traits<rnd_state>;
-    if (traits::alias)
-        fprintf(stderr, "nmch_b200: curandStateMRG32k3a_t is not on the hot path; using the native Philox stream\n");
     nmch_params_t p{};
     p.NTPB = NTPB; p.NB = NB;
     p.T = T; p.S_0 = S_0; p.v_0 = v_0; p.r = r; p.k = k; p.rho = rho; p.theta = theta; p.sigma = sigma;
@@ -66,6 +64,7 @@ void NMCH<rnd_state>::engine_init(int method, unsigned long long seed, float *ti
     switch (traits::mode) {
     case nmch::random::stream_mode::xorwow_compat: p.rng = NMCH_RNG_XORWOW_COMPAT; break;
     case nmch::random::stream_mode::philox_compat: p.rng = NMCH_RNG_PHILOX_COMPAT; break;
+    case nmch::random::stream_mode::mrg32k3a_compat: p.rng = NMCH_RNG_MRG32K3A_COMPAT; break;
     default: p.rng = philox_compat ? NMCH_RNG_PHILOX_COMPAT : NMCH_RNG_PHILOX; break;
     }
     p.device = -1;

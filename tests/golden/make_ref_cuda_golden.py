@@ -24,6 +24,9 @@ CASES = [
     dict(method="fe", rng="xorwow", kernel="k3", NTPB=512, NB=512, N=1000, k=2.08, theta=0.108, sigma=1.0, repeat=2),
     dict(method="fe", rng="xorwow", kernel="k3", NTPB=512, NB=64, N=365, T=0.5, S_0=2.0, v_0=0.04, r=0.03, k=1.5, rho=0.3,
          theta=0.09, sigma=0.5, repeat=2),
+    dict(method="fe", rng="mrg", kernel="k3", NTPB=512, NB=512, N=1000, repeat=2),
+    dict(method="fe", rng="mrg", kernel="k3", NTPB=128, NB=64, N=333, k=2.08, theta=0.108, sigma=1.0, repeat=2),
+    dict(method="em", rng="mrg", kernel="k3", NTPB=512, NB=64, N=500, repeat=2),
     dict(method="em", rng="xorwow", kernel="k3", NTPB=512, NB=64, N=1000, repeat=2),
     dict(method="em", rng="philox", kernel="k3", NTPB=512, NB=64, N=1000, repeat=2),
     dict(method="em", rng="xorwow", kernel="k3", NTPB=32, NB=4, N=100, repeat=2),

@@ -54,7 +54,7 @@ def _rel(a, b):
 # ---------------------------------------------------------------------------------------------
 # compat vs oracle and vs the reference CUDA build
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rng_e,rng_o", [(1, o.RNG_XORWOW), (2, o.RNG_PHILOX)])
+@pytest.mark.parametrize("rng_e,rng_o", [(1, o.RNG_XORWOW), (2, o.RNG_PHILOX), (3, o.RNG_MRG32K3A)])
 def test_compat_tracks_oracle(rng_e, rng_o):
     n, N = 2048, 100
     with em_engine(n, N, rng=rng_e) as e:
@@ -67,7 +67,7 @@ def test_compat_tracks_oracle(rng_e, rng_o):
     assert abs(m.mean - ref["mean"]) < 0.5 * se
 
 
-@pytest.mark.parametrize("rng_name,rng_e", [("xorwow", 1), ("philox", 2)])
+@pytest.mark.parametrize("rng_name,rng_e", [("xorwow", 1), ("philox", 2), ("mrg", 3)])
 @pytest.mark.parametrize("cfg", [dict(NTPB=512, NB=64, N=1000), dict(NTPB=128, NB=32, N=250),
                                  dict(NTPB=512, NB=32, N=500, k=2.08, theta=0.108, sigma=1.0)])
 def test_compat_matches_reference_cuda_build(rng_name, rng_e, cfg):
@@ -165,7 +165,7 @@ def test_native_deterministic_sharded_and_streams_advance():
     assert abs(parts[0].sum_payoff + parts[1].sum_payoff - a.sum_payoff) < 1e-9 * n
 
 
-@pytest.mark.parametrize("rng", [0, 1, 2])
+@pytest.mark.parametrize("rng", [0, 1, 2, 3])
 def test_explore_equals_sequential_computes(rng):
     k, th, sg = o.exploration_grid(5, apply_filter=True)
     sel = [0, 7, 40, 120, 199]

@@ -44,7 +44,7 @@ def run_engine(n, N=1000, rng=None, floor=0, seed=1234, calls=1, paths=False, **
 # ---------------------------------------------------------------------------------------------
 # compat modes vs the oracle
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rng_e,rng_o", [(1, o.RNG_XORWOW), (2, o.RNG_PHILOX)])
+@pytest.mark.parametrize("rng_e,rng_o", [(1, o.RNG_XORWOW), (2, o.RNG_PHILOX), (3, o.RNG_MRG32K3A)])
 @pytest.mark.parametrize("floor", [0, 1])
 def test_compat_per_path_matches_oracle(rng_e, rng_o, floor):
     n, N = 4096, 200
@@ -106,7 +106,7 @@ def _rel(a, b):
     return abs(a - b) / abs(b)
 
 
-@pytest.mark.parametrize("rng_name,rng_e", [("xorwow", 1), ("philox", 2)])
+@pytest.mark.parametrize("rng_name,rng_e", [("xorwow", 1), ("philox", 2), ("mrg", 3)])
 @pytest.mark.parametrize("cfg", [dict(NTPB=512, NB=512, N=1000), dict(NTPB=128, NB=64, N=333),
                                  dict(NTPB=512, NB=512, N=1000, k=2.08, theta=0.108, sigma=1.0)])
 def test_compat_matches_reference_cuda_build(rng_name, rng_e, cfg):
@@ -220,7 +220,7 @@ def test_ragged_path_counts():
 # ---------------------------------------------------------------------------------------------
 # exploration grid in one launch == sequential set_params + compute
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rng", [0, 1, 2])
+@pytest.mark.parametrize("rng", [0, 1, 2, 3])
 def test_explore_equals_sequential_computes(rng):
     k, th, sg = o.exploration_grid(5, apply_filter=True)
     k, th, sg = k[:12], th[:12], sg[:12]

@@ -17,8 +17,6 @@ def test_get_err_formula_and_true_price_line():
 
 def test_unsupported_tag_is_loud():
     from nmch_b200 import methods as M
-    with pytest.raises(NotImplementedError):
-        M.NMCH_FE_K3_MM(512, 8, 1.0, 1.0, 0.1, 0.0, 0.5, -0.7, 0.1, 0.3, 100, M.MRG32K3A)
     with pytest.raises(ValueError):
         M.NMCH_FE_K3_MM(512, 8, 1.0, 1.0, 0.1, 0.0, 0.5, -0.7, 0.1, 0.3, 100, "curandStateSobol32_t")
 

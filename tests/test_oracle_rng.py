@@ -53,6 +53,13 @@ def test_xorwow_init_matches_curand(gold):
         assert [d] + v == e["state"], e
 
 
+def test_mrg32k3a_init_matches_curand(gold):
+    # seed scramble + 3x3 matrix-power skip-ahead (2^76 draws per subsequence) == cuRAND's tables
+    for e in gold["mrg_init"]:
+        r = o.Rng(o.RNG_MRG32K3A, e["seed"], e["subseq"], e["offset"])
+        assert r.mrg_state == e["state"], e
+
+
 def test_u32_streams_match_curand(gold):
     for e in gold["u32"]:
         r = o.Rng(e["kind"], e["seed"], e["subseq"], e["offset"])

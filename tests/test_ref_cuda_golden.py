@@ -26,7 +26,7 @@ def _rel(a, b):
 def test_oracle_fe_reproduces_reference_cuda(case):
     f = case["flags"]
     n = f["NTPB"] * f["NB"]
-    rng = o.RNG_XORWOW if f["rng"] == "xorwow" else o.RNG_PHILOX
+    rng = {"xorwow": o.RNG_XORWOW, "philox": o.RNG_PHILOX, "mrg": o.RNG_MRG32K3A}[f["rng"]]
     for call, want in enumerate(case["calls"], start=1):
         got = o.fe_run(_params(f), rng=rng, n_paths=n, calls=call)
         # host libm vs device __sincosf/logf: per-path 1e-6, averaged out; the reference's float atomics add ~3e-7
@@ -52,7 +52,7 @@ def test_oracle_em_tracks_reference_cuda(case):
     n = f["NTPB"] * f["NB"]
     if n * f["N"] > 4e7:
         pytest.skip("large EM case: covered on the GPU")
-    rng = o.RNG_XORWOW if f["rng"] == "xorwow" else o.RNG_PHILOX
+    rng = {"xorwow": o.RNG_XORWOW, "philox": o.RNG_PHILOX, "mrg": o.RNG_MRG32K3A}[f["rng"]]
     got = o.em_run(_params(f), rng=rng, n_paths=n)
     want = case["calls"][0]
     se = o.std_error(got["mean"], got["mean_sq"], n)
@@ -68,7 +68,8 @@ def test_engine_compat_reproduces_reference_cuda(case):
     f = case["flags"]
     kw = {k: f[k] for k in PKEYS if k in f}
     with E.Engine(NTPB=f["NTPB"], NB=f["NB"], N=f["N"], method=E.METHOD_FE if f["method"] == "fe" else E.METHOD_EM,
-                  rng=E.RNG_XORWOW_COMPAT if f["rng"] == "xorwow" else E.RNG_PHILOX_COMPAT, **kw) as e:
+                  rng={"xorwow": E.RNG_XORWOW_COMPAT, "philox": E.RNG_PHILOX_COMPAT, "mrg": E.RNG_MRG32K3A_COMPAT}[f["rng"]],
+                  **kw) as e:
         e.init(1234)
         for want in case["calls"]:
             m = e.compute()
