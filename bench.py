@@ -300,7 +300,7 @@ def main():
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 16,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": info["kernel_param_bytes"], "d2h_bytes_per_step": 16,
                     "api": "nmch_engine_compute (C ABI)" if world == 1 else "nmch_engine_compute_async + NCCL allreduce + D2H"},
             "gpu_launches": int(launches),
             "clocks": ck,

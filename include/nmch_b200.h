@@ -118,6 +118,7 @@ void nmch_engine_destroy(nmch_engine_t *e);
 float nmch_engine_init_ms(const nmch_engine_t *e);
 typedef struct {
     int grid_x, grid_y, block_threads, paths_per_thread, regs_per_thread, sm_count;
+    int kernel_param_bytes;                 /* bytes of kernel parameters uploaded by the last launch (the only H2D traffic of compute()) */
     unsigned long long kernel_launches;     /* kernels launched by this handle so far */
 } nmch_launch_info_t;
 int nmch_engine_launch_info(const nmch_engine_t *e, nmch_launch_info_t *out);

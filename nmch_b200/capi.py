@@ -37,7 +37,7 @@ class NmchStrikeMoments(C.Structure):
 class NmchLaunchInfo(C.Structure):
     _fields_ = [("grid_x", C.c_int), ("grid_y", C.c_int), ("block_threads", C.c_int),
                 ("paths_per_thread", C.c_int), ("regs_per_thread", C.c_int), ("sm_count", C.c_int),
-                ("kernel_launches", C.c_ulonglong)]
+                ("kernel_param_bytes", C.c_int), ("kernel_launches", C.c_ulonglong)]
 
 
 EXPORTS = [

@@ -9,8 +9,9 @@ namespace nmchb {
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10.  Counter layout follows cuRAND (curand_kernel.h:1022-1037): ctr = (block_lo,
 // block_hi, path_lo, path_hi), key = seed.  The ten round keys depend only on the seed, so the
-// host expands them once and they travel in the kernel parameter block: after unrolling, every
-// key is a constant-bank operand of the LOP3 that consumes it -- no key registers, no key adds.
+// host expands them once and they travel in the kernel parameter block: after unrolling, ptxas
+// keeps every key in a uniform register that the consuming LOP3 reads directly -- no per-thread
+// key registers, no key additions in the loop.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
 constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;

@@ -151,6 +151,11 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                 const float t = z + sqrt_approx(pc.two_lc * V);
                 gsum = fmaf(0.5f * t, t, gam);
             } else {
+                // Poisson mixture: first a Poisson draw (one trial per block), then, on a block of its own, one
+                // Marsaglia-Tsang trial for Gamma(d + N).  A lane that already holds N uses this iteration's block
+                // for the gamma trial directly, so a gamma retry never re-draws (and never biases) N.
+                U4 wg = w;
+                bool gamma_now = have_np;
                 if (!have_np) {
                     const float mu = pc.lc * V;
                     if (mu < 10.0f) {
@@ -159,22 +164,25 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                     } else {
                         have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), np);
                     }
+                    if (have_np) {
+                        wg = next_block(blk++);
+                        gamma_now = true;
+                    }
                 }
                 accept = false;
                 gsum = 0.0f;
-                if (have_np) {
-                    const U4 w2 = next_block(blk++);
+                if (gamma_now) {
                     float x, unused;
-                    box_muller_fast(w2.x, w2.y, x, unused);
+                    box_muller_fast(wg.x, wg.y, x, unused);
                     float shape = pc.d + np, boost = 1.0f;
                     if (shape < 1.0f) {
-                        boost = ex2_approx(lg2_approx(u01_open(w2.w)) / shape);
+                        boost = ex2_approx(lg2_approx(u01_open(wg.w)) / shape);
                         shape += 1.0f;
                     }
                     const float md = shape - (1.0f / 3.0f);
                     const float mc = rsqrt_approx(9.0f * md);
                     float gam;
-                    accept = mt_trial(x, u01_open(w2.z), md, mc, gam);
+                    accept = mt_trial(x, u01_open(wg.z), md, mc, gam);
                     gsum = gam * boost;
                 }
             }
@@ -389,7 +397,7 @@ cudaError_t launch_fe_compat_mrg(const FeLaunch &L, int floor_kind, const RawPoi
         fe_compat_mrg_kernel<kFloorPlus><<<(unsigned)L.blocks_per_point, 256, 0, stream>>>(L, d_pts, st, rb, S_out, V_out);
         cudaFuncGetAttributes(&attr, fe_compat_mrg_kernel<kFloorPlus>);
     }
-    if (info) *info = KernelInfo{L.blocks_per_point, 1, 256, 1, attr.numRegs};
+    if (info) *info = KernelInfo{L.blocks_per_point, 1, 256, 1, attr.numRegs, (int)(sizeof(FeLaunch) + 56)};
     return cudaGetLastError();
 }
 
@@ -500,7 +508,8 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
         }
         err = cudaGetLastError();
         if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_native_kernel", err);
-        e->kinfo = KernelInfo{(int)grid.x, (int)grid.y, 256, 1, attr.numRegs};
+        e->kinfo = KernelInfo{(int)grid.x, (int)grid.y, 256, 1, attr.numRegs,
+                              (int)(sizeof(EmLaunch) + sizeof(const EmPoint *) + sizeof(ReduceBuffers) + 2 * sizeof(float *))};
         e->em_calls += (unsigned long long)n_points;
         return NMCH_OK;
     }
@@ -543,7 +552,7 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_compat_kernel", err);
-    e->kinfo = KernelInfo{(int)bpp, 1, 256, 1, attr.numRegs};
+    e->kinfo = KernelInfo{(int)bpp, 1, 256, 1, attr.numRegs, (int)(sizeof(EmCompatLaunch) + 64)};
     return NMCH_OK;
 }
 

@@ -63,7 +63,7 @@ struct DeviceGuard {
 
 namespace {
 
-bool is_pow2_or_mult(unsigned long long v, unsigned long long m) { return (v % m) == 0ull; }
+bool is_multiple_of(unsigned long long v, unsigned long long m) { return (v % m) == 0ull; }
 
 int pick_paths_per_thread(const nmch_engine *e, int n_points)
 {
@@ -132,7 +132,7 @@ int ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, siz
         e->d_tickets = nullptr;
         e->tickets_cap = 0;
         CU_TRY(cudaMalloc(&e->d_tickets, n_points * sizeof(unsigned int)));
-        CU_TRY(cudaMemsetAsync(e->d_tickets, 0, n_points * sizeof(unsigned int), e->stream));
+        CU_TRY(cudaMemset(e->d_tickets, 0, n_points * sizeof(unsigned int)));   // blocking: the next launch may be on any stream
         e->tickets_cap = n_points;
     }
     if (2 * n_points > e->out_cap) {
@@ -273,7 +273,7 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (p.first_path > n) return fail(NMCH_ERR_ARG, "first_path beyond n_paths");
     unsigned long long n_local = p.n_local ? p.n_local : n - p.first_path;
     if (n_local == 0 || p.first_path + n_local > n) return fail(NMCH_ERR_ARG, "empty or out-of-range shard");
-    if (p.rng == NMCH_RNG_PHILOX && !is_pow2_or_mult(p.first_path, kMaxTilePaths))
+    if (p.rng == NMCH_RNG_PHILOX && !is_multiple_of(p.first_path, kMaxTilePaths))
         return fail(NMCH_ERR_ARG, "native Philox mode needs first_path to be a multiple of 4096");
     if (p.paths_per_thread != 0 && p.paths_per_thread != 1 && p.paths_per_thread != 2 && p.paths_per_thread != 4 &&
         p.paths_per_thread != 8)
@@ -558,6 +558,7 @@ int nmch_engine_launch_info(const nmch_engine_t *e, nmch_launch_info_t *out)
     out->paths_per_thread = e->kinfo.paths_per_thread;
     out->regs_per_thread = e->kinfo.regs_per_thread;
     out->sm_count = e->sm_count;
+    out->kernel_param_bytes = e->kinfo.param_bytes;
     out->kernel_launches = e->launches;
     return NMCH_OK;
 }

@@ -14,7 +14,7 @@ struct nmch_engine {
     unsigned long long draw_offset = 0;      // FE Philox modes: u32 words consumed per path so far
     unsigned long long em_calls = 0;         // EM native mode: compute() calls so far (selects a fresh stream)
     float init_ms = 0.0f;
-    int P = 4, threads = 256;
+    int threads = 128;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // reduction buffers

@@ -5,7 +5,8 @@
 // reproduces the reference's cuRAND streams and IEEE arithmetic draw for draw.
 //
 // Native kernel, per path-step (see DESIGN.md §Kernels for the instruction budget):
-//   * half a Philox4x32-10 block (the block serves two steps; round keys are constant-bank operands)
+//   * half a Philox4x32-10 block (the block serves two steps; round keys sit in uniform registers, the
+//     counter-invariant part of rounds 1-2 is hoisted per path)
 //   * u32 -> float by bit splicing (ALU pipe, no I2F on the XU pipe)
 //   * Box-Muller with MUFU.LG2 / MUFU.SIN / MUFU.COS and ONE MUFU.SQRT shared with the SDE:
 //       sqrt(V)*sqrt(-2 ln u) = c0 * sqrt(-V * lg2 u),  c0 = sqrt(2 ln 2) folded into host constants
@@ -165,6 +166,7 @@ static cudaError_t launch_philox_t(const FeLaunch &L, int block_threads, const F
         info->block_threads = block_threads == 128 ? 128 : 256;
         info->paths_per_thread = P;
         info->regs_per_thread = attr.numRegs;
+        info->param_bytes = (int)(sizeof(FeLaunch) + sizeof(const FePoint *) + sizeof(ReduceBuffers) + 2 * sizeof(float *));
     }
     const cudaError_t lerr = cudaGetLastError();
     return lerr != cudaSuccess ? lerr : err;
@@ -311,6 +313,7 @@ cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind, in
         info->block_threads = threads;
         info->paths_per_thread = 1;
         info->regs_per_thread = attr.numRegs;
+        info->param_bytes = (int)(sizeof(FeLaunch) + sizeof(const RawPoint *) + sizeof(XorwowState) + sizeof(ReduceBuffers) + 2 * sizeof(float *));
     }
     const cudaError_t lerr = cudaGetLastError();
     return lerr != cudaSuccess ? lerr : err;

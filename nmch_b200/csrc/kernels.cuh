@@ -57,6 +57,7 @@ struct XorwowState {                    // structure of arrays, one entry per lo
 
 struct KernelInfo {
     int grid_x, grid_y, block_threads, paths_per_thread, regs_per_thread;
+    int param_bytes = 0;
 };
 
 // fe_kernels.cu
