@@ -34,6 +34,12 @@ struct EmPoint {
     float a;            // fast path: gamma shape d - 1/2 (boosted by +1 when < 1)
     float mt_d, mt_c;   // Marsaglia-Tsang constants of the fast path's gamma
     float inv_a;        // 1/a when boosting, else 0
+    // fast path with every constant folded (normals are produced as n' = n / c0, c0 = sqrt(2 ln 2)):
+    float f_c;          // mt_c * c0
+    float f_h;          // 0.5 * c0^2 * log2(e)    log test, log2 domain
+    float f_dl;         // mt_d * log2(e)
+    float f_g2;         // 2 * mt_d                gamma term of 2 * (V'/c)
+    float f_scale;      // c / 2
     float k, ktheta_T, inv_sigma;
     int   fast;         // 1: d - 1/2 > 0, chi-square split; 0: Poisson-mixture path
 };
@@ -144,12 +150,23 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
             float gsum;
             bool accept;
             if (!MIXED || pc.fast) {
-                float z, x, gam;
-                box_muller_fast(w.x, w.y, z, x);
-                accept = mt_trial(x, u01_open(w.z), pc.mt_d, pc.mt_c, gam);
-                if (pc.inv_a != 0.0f) gam *= ex2_approx(pc.inv_a * lg2_approx(u01_open(w.w)));   // shape < 1 boost
-                const float t = z + sqrt_approx(pc.two_lc * V);
-                gsum = fmaf(0.5f * t, t, gam);
+                // chi-square split, every constant folded on the host, no data-dependent branch:
+                //   2 V'/c = (Z + sqrt(2 l))^2 + 2 Gamma(a),   Z = c0 z', X = c0 x' from one Box-Muller pair
+                const float rad = sqrt_approx(-lg2_approx(u01_open(w.x)));
+                const float ang = bits_to_1_2(w.y) * 6.2831855f;
+                const float zp = rad * sin_approx(ang), xp = rad * cos_approx(ang);
+                // Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp: accept iff v1 > 0 and
+                //   log2 u < (x^2/2 + d (1 - v)) log2 e + d log2 v      (the exact test; no squeeze, no divergence)
+                const float v1 = fmaf(pc.f_c, xp, 1.0f);
+                const float v = v1 * v1 * v1;
+                const float x2 = xp * xp;
+                float rhs = fmaf(x2, pc.f_h, pc.f_dl * (1.0f - v));
+                rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
+                accept = (v1 > 0.0f) && (lg2_approx(u01_open(w.z)) < rhs);
+                float g2 = pc.f_g2 * v;
+                if (pc.inv_a != 0.0f) g2 *= ex2_approx(pc.inv_a * lg2_approx(u01_open(w.w)));   // shape < 1 boost
+                const float t = fmaf(1.17741002f, zp, sqrt_approx(pc.two_lc * V));
+                gsum = fmaf(t, t, g2);                          // = 2 V'/c
             } else {
                 // Poisson mixture: first a Poisson draw (one trial per block), then, on a block of its own, one
                 // Marsaglia-Tsang trial for Gamma(d + N).  A lane that already holds N uses this iteration's block
@@ -183,11 +200,11 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                     const float mc = rsqrt_approx(9.0f * md);
                     float gam;
                     accept = mt_trial(x, u01_open(wg.z), md, mc, gam);
-                    gsum = gam * boost;
+                    gsum = 2.0f * gam * boost;                  // same convention as the split: gsum = 2 V'/c
                 }
             }
             if (accept) {
-                const float Vn = __fmul_rn(pc.scale, gsum);    // explicit roundings: both instantiations agree bit for bit
+                const float Vn = __fmul_rn(pc.f_scale, gsum);  // explicit roundings: both instantiations agree bit for bit
                 vI = __fadd_rn(vI, __fadd_rn(V, Vn));          // trapezoid sum, NMCH_EM.cu:243
                 V = Vn;
                 ++step;
@@ -425,6 +442,12 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
         pt.mt_d = (float)md;
         pt.mt_c = (float)(1.0 / std::sqrt(9.0 * md));
     }
+    const double c0 = 1.1774100225154747, log2e = 1.4426950408889634;
+    pt.f_c = (float)(pt.mt_c * c0);
+    pt.f_h = (float)(0.5 * c0 * c0 * log2e);
+    pt.f_dl = (float)(pt.mt_d * log2e);
+    pt.f_g2 = 2.0f * pt.mt_d;
+    pt.f_scale = 0.5f * pt.scale;
     pt.k = kf;
     pt.ktheta_T = (float)(k * theta * (double)p.T);
     pt.inv_sigma = (float)(1.0 / sigma);
