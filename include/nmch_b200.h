@@ -28,8 +28,10 @@ typedef enum {
     NMCH_ERR_NCCL = -4
 } nmch_status;
 
-/* which scheme: FE = NMCH_FE_* (src/NMCH/methods/NMCH_FE.cu), EM = NMCH_EM_* (NMCH_EM.cu) */
-typedef enum { NMCH_METHOD_FE = 0, NMCH_METHOD_EM = 1 } nmch_method;
+/* which scheme: FE = NMCH_FE_* (src/NMCH/methods/NMCH_FE.cu), EM = NMCH_EM_* (NMCH_EM.cu);
+ * QE = Andersen's quadratic-exponential large-step scheme with martingale correction (no reference equivalent:
+ * SURVEY.md §8f row 3), native Philox stream only */
+typedef enum { NMCH_METHOD_FE = 0, NMCH_METHOD_EM = 1, NMCH_METHOD_QE = 2 } nmch_method;
 /* variance floor g(.) of README.md:37-40; the reference codes only ABS (NMCH_FE.cu:162) */
 typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
 /* stream mode, selected by the reference's rnd_state template tag:

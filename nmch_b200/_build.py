@@ -18,7 +18,7 @@ BIN = os.path.join(ROOT, "bin")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
-CU_SOURCES = ["engine.cu", "fe_kernels.cu", "em_kernels.cu", "xorwow.cu", "group.cu", "strike_kernels.cu"]
+CU_SOURCES = ["engine.cu", "fe_kernels.cu", "em_kernels.cu", "xorwow.cu", "group.cu", "strike_kernels.cu", "qe_kernels.cu"]
 
 
 def _newer(target: str, deps) -> bool:
@@ -66,7 +66,7 @@ def build_cli(force: bool = False, verbose: bool = False):
     os.makedirs(BIN, exist_ok=True)
     cxx = "/usr/bin/g++"
     outs = []
-    api = [os.path.join(src_dir, "NMCH", "methods", f) for f in ("NMCH.cpp", "NMCH_FE.cpp", "NMCH_EM.cpp")]
+    api = [os.path.join(src_dir, "NMCH", "methods", f) for f in ("NMCH.cpp", "NMCH_FE.cpp", "NMCH_EM.cpp", "NMCH_QE.cpp")]
     api += [os.path.join(src_dir, "NMCH", "utils", "utils.cpp")]
     for name in ("nmch", "exploration"):
         main = os.path.join(src_dir, "NMCH", "test", f"{name}.cpp")

@@ -6,7 +6,7 @@ import os
 
 from . import _build
 
-METHOD_FE, METHOD_EM = 0, 1
+METHOD_FE, METHOD_EM, METHOD_QE = 0, 1, 2
 FLOOR_ABS, FLOOR_PLUS = 0, 1
 RNG_PHILOX, RNG_XORWOW_COMPAT, RNG_PHILOX_COMPAT, RNG_MRG32K3A_COMPAT = 0, 1, 2, 3
 

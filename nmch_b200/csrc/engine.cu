@@ -220,8 +220,11 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                 CU_TRY(launch_fe_compat(L, p.rng, p.floor, 256, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
         }
         e->draw_offset += 2ull * (unsigned long long)p.N * (unsigned long long)n_points;
-    } else {
+    } else if (p.method == NMCH_METHOD_EM) {
         int rc = em_launch_points(e, stream, k, theta, sigma, n_points, d_out, S_out, V_out);
+        if (rc) return rc;
+    } else {
+        int rc = qe_launch_points(e, stream, k, theta, sigma, n_points, d_out, S_out, V_out);
         if (rc) return rc;
     }
     e->launches += 1;
@@ -262,7 +265,10 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (!params || !out) return fail(NMCH_ERR_ARG, "null argument");
     const nmch_params_t &p = *params;
     if (p.N <= 0) return fail(NMCH_ERR_ARG, "N must be positive");
-    if (p.method != NMCH_METHOD_FE && p.method != NMCH_METHOD_EM) return fail(NMCH_ERR_ARG, "unknown method");
+    if (p.method != NMCH_METHOD_FE && p.method != NMCH_METHOD_EM && p.method != NMCH_METHOD_QE)
+        return fail(NMCH_ERR_ARG, "unknown method");
+    if (p.method == NMCH_METHOD_QE && p.rng != NMCH_RNG_PHILOX)
+        return fail(NMCH_ERR_ARG, "the QE scheme has no reference counterpart to be draw-compatible with: use rng = PHILOX");
     if (p.floor != NMCH_FLOOR_ABS && p.floor != NMCH_FLOOR_PLUS) return fail(NMCH_ERR_ARG, "unknown floor");
     if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_MRG32K3A_COMPAT) return fail(NMCH_ERR_ARG, "unknown rng mode");
     unsigned long long n = p.n_paths;

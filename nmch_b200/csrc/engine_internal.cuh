@@ -45,6 +45,9 @@ int engine_ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_poi
 // em_kernels.cu
 int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
                      int n_points, double *d_out, float *S_out, float *V_out);
+// qe_kernels.cu
+int qe_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
+                     int n_points, double *d_out, float *S_out, float *V_out);
 int em_philox_compat_init(nmch_engine *e);
 int mrg_compat_init(nmch_engine *e);
 cudaError_t launch_fe_compat_mrg(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, void *states,

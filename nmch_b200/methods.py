@@ -148,3 +148,9 @@ class NMCH_EM_K1(NMCH):
 class NMCH_EM_K1_MM(NMCH_EM_K1): pass
 class NMCH_EM_K2_MM(NMCH_EM_K1_MM): pass
 class NMCH_EM_K3_MM(NMCH_EM_K2_MM): pass
+
+
+class NMCH_QE_K1_MM(NMCH):
+    """Third method (no reference counterpart): Andersen's QE-M large-step scheme; native Philox tag only."""
+    _method = _eng.METHOD_QE
+    _title = "QUADRATIC-EXPONENTIAL"

@@ -738,6 +738,65 @@ void orc_em_exact_run(const orc_params_t *p, uint64_t seed, uint64_t n_paths,
 }
 
 /* ======================================================================== */
+/* QE-M (Andersen 2008), the product's third method: no reference counterpart */
+/* ======================================================================== */
+/* Restates nmch_b200/csrc/qe_kernels.cu on the SAME draws (one Philox block per (path, step), counter =
+ * (step, call, path_lo, path_hi), 23-bit uniforms) with libm in place of the MUFU approximations, so the kernel can
+ * be checked path by path; the scheme itself is checked against the semi-analytic price in the tests. */
+void orc_qe_run(const orc_params_t *p, uint64_t seed, uint64_t first_path, uint64_t n_paths, uint32_t call,
+                float *S_out, float *V_out, double *sum, double *sumsq, int threads)
+{
+    const double k = p->k, theta = p->theta, sigma = p->sigma, rho = p->rho, dt = (double)p->T / p->N;
+    const double e = exp(-k * dt), om = -expm1(-k * dt);
+    const float fe = (float)e, m0 = (float)(theta * om), c1 = (float)(sigma * sigma * e * om / k),
+                c2 = (float)(theta * sigma * sigma * om * om / (2.0 * k));
+    const double dK2 = 0.5 * dt * (k * rho / sigma - 0.5) + rho / sigma, dK3 = 0.5 * dt * (1.0 - rho * rho);
+    const float K2 = (float)dK2, K3 = (float)dK3, K4 = (float)dK3, A = (float)(dK2 + 0.5 * dK3);
+    const float r_dt = p->r * (p->T / (float)p->N), lnS0 = (float)log((double)p->S_0), K = p->S_0;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    double acc = 0.0, acc2 = 0.0;
+    if (threads <= 0) threads = orc_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc, acc2) num_threads(threads) schedule(static)
+#endif
+    for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+        const uint64_t g = first_path + (uint64_t)i;
+        float V = p->v_0, lnS = lnS0;
+        for (int n = 0; n < p->N; ++n) {
+            const uint32_t ctr[4] = {(uint32_t)n, call, (uint32_t)g, (uint32_t)(g >> 32)};
+            uint32_t w[4];
+            orc_philox4x32_10(ctr, key, w);
+            const float u1 = ((float)(w[0] >> 9) + 0.5f) * 1.1920929e-07f;
+            const float rad = sqrtf(-2.0f * logf(u1));
+            const float ang = (1.0f + (float)(w[1] >> 9) * 1.1920929e-07f) * 6.2831855f;
+            const float zv = rad * sinf(ang), zs = rad * cosf(ang);
+            const float u = ((float)(w[2] >> 9) + 0.5f) * 1.1920929e-07f;
+            const float m = fmaf(V, fe, m0), s2 = fmaf(V, c1, c2), psi = s2 / (m * m);
+            float Vn, lnM;
+            if (psi <= 1.5f) {
+                const float t = 2.0f / psi, b2 = t - 1.0f + sqrtf(t * (t - 1.0f)), a = m / (1.0f + b2);
+                const float q = sqrtf(b2) + zv, den = 1.0f - 2.0f * A * a;
+                Vn = a * q * q;
+                lnM = A * b2 * a / den - 0.5f * logf(den);
+            } else {
+                const float pp = (psi - 1.0f) / (psi + 1.0f), beta = (1.0f - pp) / m;
+                Vn = (u <= pp) ? 0.0f : logf((1.0f - pp) / (1.0f - u)) / beta;
+                lnM = logf(pp + beta * (1.0f - pp) / (beta - A));
+            }
+            lnS += r_dt - lnM - 0.5f * K3 * V + K2 * Vn + sqrtf(fmaf(K3, V, K4 * Vn)) * zs;
+            V = Vn;
+        }
+        const float S = expf(lnS), pay = fmaxf(0.0f, S - K);
+        acc += (double)pay;
+        acc2 += (double)pay * (double)pay;
+        if (S_out) S_out[i] = S;
+        if (V_out) V_out[i] = V;
+    }
+    if (sum) *sum = acc;
+    if (sumsq) *sumsq = acc2;
+}
+
+/* ======================================================================== */
 /* host statistics                                                           */
 /* ======================================================================== */
 float orc_get_err(int state_numbers, float strike_price, float price_squared)

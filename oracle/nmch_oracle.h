@@ -93,6 +93,11 @@ void orc_em_run(const orc_params_t *p, int rng_kind, uint64_t seed,
 void orc_em_exact_run(const orc_params_t *p, uint64_t seed, uint64_t n_paths,
                       double *sum, double *sumsq, double *sum_ST, int threads);
 
+/* --- QE-M, the product's large-step third method (no reference counterpart): restates the KERNEL's scheme and
+ * draw mapping (nmch_b200/csrc/qe_kernels.cu) with libm, for per-path checks; `call` is the engine's call counter */
+void orc_qe_run(const orc_params_t *p, uint64_t seed, uint64_t first_path, uint64_t n_paths, uint32_t call,
+                float *S_out, float *V_out, double *sum, double *sumsq, int threads);
+
 /* --- host statistics ------------------------------------------------------ */
 /* include/NMCH/methods/NMCH_FE.hpp:50-55 (float/double mix reproduced) */
 float  orc_get_err(int state_numbers, float strike_price, float price_squared);

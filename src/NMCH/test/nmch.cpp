@@ -13,6 +13,7 @@
 
 #include "NMCH/methods/NMCH_EM.hpp"
 #include "NMCH/methods/NMCH_FE.hpp"
+#include "NMCH/methods/NMCH_QE.hpp"
 
 using namespace nmch::methods;
 
@@ -46,6 +47,7 @@ void usage(const char *argv0)
     printf("  --method <string>  Method to use: fe or em (default: fe)\n");
     printf("  --help             Display this help message\n");
     printf("B200 engine options (actual defaults: NTPB 512, NB 512, N 1000):\n");
+    printf("  --method qe        Quadratic-exponential large-step scheme (use with --N 50..100)\n");
     printf("  --g <abs|plus>     Variance floor g(.) (default: abs)\n");
     printf("  --rng <philox|xorwow|philox-compat>  Stream mode (default: philox)\n");
     printf("  --gpus <int>       GPUs to shard the paths over (default: 1)\n");
@@ -67,13 +69,13 @@ int run(const Options &o)
     m.print_stats();
     if (o.json) {
         const double n = (double)o.NTPB * (double)o.NB;
-        const double units = o.method == "fe" ? n * o.N : n;
+        const double units = o.method == "em" ? n : n * o.N;
         printf("{\"method\": \"%s\", \"rng\": \"%s\", \"floor\": \"%s\", \"gpus\": %d, \"n_paths\": %.0f, \"N\": %d, "
                "\"sum_payoff\": %.17g, \"sum_payoff_sq\": %.17g, \"E\": %.9g, \"E2\": %.9g, \"std_error\": %.6g, "
                "\"err\": %.9g, \"exec_ms\": %.6f, \"%s\": %.6g}\n",
                o.method.c_str(), o.rng.c_str(), o.g.c_str(), o.gpus, n, o.N, m.get_sum_payoff(), m.get_sum_payoff_sq(),
                m.get_strike_price(), m.get_price_squared(), m.get_std_error(), m.get_err(), m.get_execution_time(),
-               o.method == "fe" ? "path_steps_per_s" : "paths_per_s", units / (m.get_execution_time() * 1e-3));
+               o.method == "em" ? "paths_per_s" : "path_steps_per_s", units / (m.get_execution_time() * 1e-3));
     }
     if (!o.strikes.empty()) {
         std::vector<float> ks;
@@ -129,6 +131,10 @@ int main(int argc, char **argv)
         return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(o);
     if (o.method == "em")
         return x ? run<NMCH_EM_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_EM_K3_MM<curandStatePhilox4_32_10_t>>(o);
+    if (o.method == "qe") {                                // additive: large-step QE-M scheme (native Philox stream only)
+        if (o.rng != "philox") { printf("Method qe needs --rng philox\n"); return 1; }
+        return run<NMCH_QE_K1_MM<curandStatePhilox4_32_10_t>>(o);
+    }
     printf("Unknown method: %s\n", o.method.c_str());      // reference nmch.cu:135-137
     return 1;
 }

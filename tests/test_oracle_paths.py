@@ -124,3 +124,13 @@ def test_exploration_grid_matches_reference_loops():
     assert np.isclose(sg[0], 0.1) and np.isclose(sg[-1], 1.0)
     assert np.isclose(k.max(), 9.999999, atol=1e-5)
     assert not np.any(20 * k * th < sg * sg)
+
+
+def test_qe_restatement_matches_semi_analytic_at_large_steps():
+    # the product's third method (no reference counterpart): the checker itself is checked against the analytic price
+    n = 1 << 16
+    for kw, want in ((dict(), 0.1197325094), (dict(k=2.08, theta=0.108, sigma=1.0), 0.1104934558)):
+        r = o.qe_run(o.Params(N=25, **kw), seed=3, n_paths=n, want_paths=True)
+        se = o.std_error(r["mean"], r["mean_sq"], n)
+        assert abs(r["mean"] - want) < 3.5 * se + 3e-4
+        assert abs(r["S"].astype(np.float64).mean() - 1.0) < 4 * r["S"].std() / np.sqrt(n)
