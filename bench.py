@@ -104,7 +104,7 @@ def cpu_baseline(method: str, N: int, budget_s: float = 12.0):
     t0 = time.perf_counter()
     run(n)
     dt = time.perf_counter() - t0
-    while dt < 1.0 and n < (1 << 24):            # find the rate, then size one sample to the budget
+    while dt < min(1.0, budget_s) and n < (1 << 24):   # find the rate, then size one sample to the budget
         n *= 4
         t0 = time.perf_counter()
         run(n)
@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=None, help="seconds of host work per CPU-baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -192,7 +193,8 @@ def main():
         base = None
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            base = cpu_baseline(args.method, N, budget_s=max(2.0, 60.0 / max(1, args.steps + args.warmup)))
+            base = cpu_baseline(args.method, N, budget_s=args.cpu_budget_s if args.cpu_budget_s is not None
+                                else max(2.0, 60.0 / max(1, args.steps + args.warmup)))
             if i >= args.warmup:
                 times.append(base["value"])
                 walls.append(time.perf_counter() - t0)
@@ -315,7 +317,7 @@ def main():
                        "heston_semi_analytic": 0.1197325094 if args.method in ("fe", "em") else None},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.method, N)
+            line["cpu_baseline"] = cpu_baseline(args.method, N, budget_s=args.cpu_budget_s or 12.0)
         if not args.no_reference_cuda and world == 1:
             line["reference_cuda"] = reference_cuda(args.method, log2_paths, N)
         print(json.dumps(line))
