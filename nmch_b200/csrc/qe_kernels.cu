@@ -5,8 +5,8 @@
 // CIR transition with either a squared shifted normal (psi <= 1.5) or a point mass at zero plus an exponential tail
 // (psi > 1.5), integrates the log-price with the central discretisation (gamma1 = gamma2 = 1/2) and fixes the drift so
 // that E[S] is exact.  It reaches the accuracy of N = 1000 Euler steps with 50-100 steps.  There is no reference
-// implementation to be draw-compatible with, so this kernel exists for the native Philox stream only; the checker
-// is the semi-analytic price and the oracle's restatement of the same scheme (oracle/nmch_oracle.c, orc_qe_run).
+// implementation to be draw-compatible with, so this kernel exists for the native Philox stream only; it is checked
+// against the semi-analytic price and a host restatement of the same scheme on the same draws (tests/test_gpu_qe.py).
 //
 // One Philox block per (path, step): words (x, y) -> Box-Muller pair (Z_v, Z_s), word z -> the uniform of the
 // exponential branch; counter = (step, call/point id, path_lo, path_hi) like the EM kernel.

@@ -6,7 +6,7 @@
   C4  exploration grid 20^3 over (k, theta, sigma), 2^20 paths per point, ONE launch per method
   C5  FE + EM at 2^30 paths, N=1000, on all visible GPUs (single-process group, one NCCL allreduce)
 
-usage: python scripts/run_configs.py [--out profiles/configs_r01.json] [--skip c4,c5] [--c4-log2-paths 20]
+usage: python tests/run_configs.py [--out profiles/configs_r01.json] [--skip c4,c5] [--c4-log2-paths 20]
 """
 import argparse
 import json
