@@ -27,9 +27,10 @@ namespace nmchb {
 int engine_fail(int status, const char *what, cudaError_t err)
 {
     char buf[512];
-    if (err != cudaSuccess)
+    if (err != cudaSuccess) {
         std::snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(err), cudaGetErrorString(err));
-    else
+        (void)cudaGetLastError();       // a failed call leaves its code behind; do not let a later launch inherit it
+    } else
         std::snprintf(buf, sizeof buf, "%s", what);
     g_last_error = buf;
     return status;
@@ -305,10 +306,23 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     return NMCH_OK;
 }
 
+static int engine_init_impl(nmch_engine_t *e, unsigned long long seed);
+
 int nmch_engine_init(nmch_engine_t *e, unsigned long long seed)
 {
     if (!e) return fail(NMCH_ERR_ARG, "null engine");
     if (e->inited) return fail(NMCH_ERR_STATE, "engine already initialised");
+    const int rc = engine_init_impl(e, seed);
+    if (rc != NMCH_OK) {
+        const std::string why = nmch_last_error();      // keep the cause: the clean-up below may overwrite it
+        nmch_engine_finalize(e);
+        engine_fail(rc, why.c_str());
+    }
+    return rc;
+}
+
+static int engine_init_impl(nmch_engine_t *e, unsigned long long seed)
+{
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
     CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -514,7 +528,8 @@ int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const
 int nmch_engine_finalize(nmch_engine_t *e)
 {
     if (!e) return fail(NMCH_ERR_ARG, "null engine");
-    if (!e->inited) return NMCH_OK;                      // idempotent (the reference double-frees)
+    // Idempotent (the reference double-frees), and also the clean-up path of an init() that failed half way:
+    // every resource is released if present, whatever the lifecycle flag says.
     DeviceGuard guard(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->d_partials) cudaFree(e->d_partials);

@@ -330,3 +330,18 @@ def test_full_size_properties_2_pow_24():
     assert abs(halves[0].sum_payoff_sq + halves[1].sum_payoff_sq - a.sum_payoff_sq) < 1e-10 * n
     assert abs(a.mean - o.heston_call()) < 3 * a.std_error + 5e-5                        # price
     assert 0 < a.variance < a.mean_sq
+
+
+def test_failed_init_cleans_up_and_reports_cause():
+    from nmch_b200 import capi
+    e = E.Engine(NTPB=1, NB=1, N=10, rng=1, n_paths=1 << 40)       # 26 TB of XORWOW state: cudaMalloc must fail
+    with pytest.raises(capi.NmchError) as ei:
+        e.init(1)
+    assert ei.value.status == capi.ERR_CUDA and "cudaMalloc" in str(ei.value)
+    with pytest.raises(capi.NmchError):
+        e.compute()
+    e.finalize()
+    e.close()
+    with E.Engine(NTPB=32, NB=4, N=10) as ok:                     # the device is still healthy
+        ok.init(1)
+        assert ok.compute().n_paths == 128
