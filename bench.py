@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 
 README = dict(T=1.0, S_0=1.0, v_0=0.1, r=0.0, k=0.5, rho=-0.7, theta=0.1, sigma=0.3)
 ISSUE_PER_CLK_PER_SM = min(128.0 / 42.0, 16.0 / 5.0)      # 42 thread-instr, 5 MUFU per path-step
+# profiles/r01_fe_mix_bound.txt: the FE kernel's own instruction mix, issued from independent chains on this GPU,
+# needs 55.04 cycles per warp-step per SM sub-partition (the Philox IMAD.WIDE.U32 costs ~5.2 issue cycles)
+MIX_BOUND_CYCLES_PER_WARP_STEP = 55.04
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,7 +314,11 @@ def main():
                          "model": "SURVEY.md §8d: SMs x f x min(128/42 issue, 16/5 MUFU) path-steps/s; f = median SM clock "
                                   "sampled during the timed region; per-GPU achieved" if args.method == "fe" else
                                   "EM has no fixed instruction budget (data-dependent samplers); FE model shown for scale",
-                         "peak_at_max_clock": info["sm_count"] * (ck["sm_max_mhz"] or 1965) * 1e6 * ISSUE_PER_CLK_PER_SM},
+                         "peak_at_max_clock": info["sm_count"] * (ck["sm_max_mhz"] or 1965) * 1e6 * ISSUE_PER_CLK_PER_SM,
+                         "mix_bound_peak": (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP
+                                            if args.method == "fe" else None),
+                         "mix_bound_frac": (per_gpu / (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP)
+                                            if args.method == "fe" else None)},
             "kernel": {k: info[k] for k in ("grid_x", "grid_y", "block_threads", "paths_per_thread", "regs_per_thread", "sm_count")},
             "result": {"E[X]": mean, "var": var, "std_error": (var / n_total) ** 0.5,
                        "heston_semi_analytic": 0.1197325094 if args.method in ("fe", "em") else None},
