@@ -223,8 +223,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout = one JSON line
+        # NCCL prints its version banner on the C-level stdout when the communicator comes up: park fd 1 on stderr
+        # until the JSON line is due, so that stdout carries exactly one line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     from nmch_b200.distributed import ShardedEngine
@@ -284,6 +289,10 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = units_per_gpu_step * world * args.steps / float(e2e_s.item())
 
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         info = eng.launch_info()
         ck = clocks.summary()

@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "../../include/nmch_b200.h"
+#include <nvtx3/nvToolsExt.h>
+
 #include "engine_internal.cuh"
 
 using namespace nmchb;
@@ -44,6 +46,12 @@ inline int fail(int status, const char *what, cudaError_t err = cudaSuccess) { r
         cudaError_t err__ = (call);                                     \
         if (err__ != cudaSuccess) return fail(NMCH_ERR_CUDA, #call, err__); \
     } while (0)
+
+// NVTX range for profilers (nsys / ncu --nvtx); header-only NVTX3, a no-op unless a tool is attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -323,6 +331,7 @@ int nmch_engine_init(nmch_engine_t *e, unsigned long long seed)
 
 static int engine_init_impl(nmch_engine_t *e, unsigned long long seed)
 {
+    NvtxRange range("nmch_engine_init");
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
     CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -378,6 +387,7 @@ int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out)
     int rc = check_ready(e);
     if (rc) return rc;
     if (!out) return fail(NMCH_ERR_ARG, "null output");
+    NvtxRange range("nmch_engine_compute");
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
     rc = ensure_buffers(e, 1, 1, 0);
@@ -411,6 +421,7 @@ int nmch_engine_explore(nmch_engine_t *e, const float *k, const float *theta, co
     if (rc) return rc;
     if (!k || !theta || !sigma || !out || n_points <= 0) return fail(NMCH_ERR_ARG, "bad exploration arguments");
     if (n_points > 65535) return fail(NMCH_ERR_ARG, "at most 65535 points per launch");
+    NvtxRange range("nmch_engine_explore");
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
     rc = ensure_buffers(e, n_points, 1, 0);
