@@ -93,8 +93,8 @@ def test_exploration_default_run_is_the_reference_sweep():
     np.testing.assert_allclose([float(x[3]) for x in fe], sg, atol=1e-6)
     # same err column as the reference build for the first points (XORWOW tag, continued streams, N = 40)
     if os.path.exists(o.REF_HARNESS_PATH):
-        pts = os.path.join(ROOT, "gpurun_out", "_sweep_pts.txt")
-        os.makedirs(os.path.dirname(pts), exist_ok=True)
+        import tempfile
+        pts = os.path.join(tempfile.mkdtemp(), "sweep_pts.txt")
         with open(pts, "w") as f:
             f.write("0.5 0.1 0.3\n")                                                 # the warm-up compute
             for i in range(8):
@@ -112,5 +112,12 @@ def test_exploration_bias_column_and_linspace_grid():
     rows = [l.split(", ") for l in r.stdout.splitlines()[1:]]
     assert r.stdout.splitlines()[0].endswith(", bias")
     assert 20 <= len(rows) <= 27
+    # the CSV is what the reference's heatmap.py consumes: columns method/k/theta/sigma/bias after stripping blanks
+    import io
+    import pandas as pd
+    df = pd.read_csv(io.StringIO(r.stdout))
+    df.columns = df.columns.str.strip()
+    assert {"method", "k", "theta", "sigma", "bias"} <= set(df.columns) and len(df) == len(rows)
+    assert pd.to_numeric(df["bias"], errors="coerce").notna().all()
     worst = max(rows, key=lambda x: abs(float(x[6])))
     assert abs(float(worst[6])) < 0.03, worst                  # Euler bias (sigma = 1 corners) + MC noise stay small
