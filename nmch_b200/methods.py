@@ -3,8 +3,9 @@
 Same class names, constructor argument order, lifecycle (init(seed) / compute() / print_stats() /
 finalize()), getters and setters as the C++ templates, so tests read like the reference's own usage
 (README.md:60-93, src/NMCH/test/nmch.cu:115-134).  The `rnd_state` template tag becomes a keyword:
-"curandStateXORWOW_t" -> cuRAND-XORWOW-compatible stream, "curandStatePhilox4_32_10_t" -> native fused
-Philox (pass compat=True for the cuRAND-Philox draw-and-arithmetic compatible validation mode).
+"curandStateXORWOW_t" -> cuRAND-XORWOW-compatible stream, "curandStateMRG32k3a_t" -> cuRAND-MRG32k3a-compatible
+stream, "curandStatePhilox4_32_10_t" -> native fused Philox (pass compat=True for the cuRAND-Philox
+draw-and-arithmetic compatible validation mode).
 All K1/K2/K3/MM/PgM/PiM variants map to the one engine (their differences were memory-space and
 reduction experiments, NMCH_FE.hpp:76-189).  No arithmetic happens here.
 """
