@@ -345,3 +345,21 @@ def test_failed_init_cleans_up_and_reports_cause():
     with E.Engine(NTPB=32, NB=4, N=10) as ok:                     # the device is still healthy
         ok.init(1)
         assert ok.compute().n_paths == 128
+
+
+def test_explore_with_several_tiles_per_block_matches_sequential():
+    # many points x many path tiles: blocks walk several tiles each (a different reduction tree than a single compute)
+    k, th, sg = o.exploration_grid(5, apply_filter=True)
+    k, th, sg = k[:3], th[:3], sg[:3]
+    n, N = 1 << 18, 40
+    with E.Engine(NTPB=512, NB=n // 512, N=N, rng=0) as e:
+        e.init(1234)
+        batched = e.explore(k, th, sg)
+        assert e.launch_info()["grid_x"] <= 256 and e.launch_info()["grid_y"] == 3
+    with E.Engine(NTPB=512, NB=n // 512, N=N, rng=0) as e:
+        e.init(1234)
+        for i in range(3):
+            e.set_params(float(k[i]), float(th[i]), float(sg[i]))
+            s = e.compute()
+            np.testing.assert_allclose([batched[i].sum_payoff, batched[i].sum_payoff_sq], [s.sum_payoff, s.sum_payoff_sq],
+                                       rtol=1e-12)
