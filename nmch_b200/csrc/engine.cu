@@ -226,7 +226,7 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
             if (p.rng == NMCH_RNG_MRG32K3A_COMPAT)
                 CU_TRY(launch_fe_compat_mrg(L, p.floor, d_pts, e->curand_states, rb, S_out, V_out, stream, &e->kinfo));
             else
-                CU_TRY(launch_fe_compat(L, p.rng, p.floor, 256, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
+                CU_TRY(launch_fe_compat(L, p.rng, p.floor, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
         }
         e->draw_offset += 2ull * (unsigned long long)p.N * (unsigned long long)n_points;
     } else if (p.method == NMCH_METHOD_EM) {

@@ -283,12 +283,11 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
     }
 }
 
-cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind, int block_threads,
+cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind,
                              const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out, float *V_out,
                              cudaStream_t stream, KernelInfo *info)
 {
-    (void)block_threads;
-    const int threads = 256;
+    const int threads = 256;                 // one path per thread; L.blocks_per_point is sized for this
     dim3 grid((unsigned)L.blocks_per_point, 1, 1);
     cudaFuncAttributes attr{};
     cudaError_t err = cudaSuccess;

@@ -64,7 +64,7 @@ struct KernelInfo {
 cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int paths_per_thread, int block_threads,
                              const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out,
                              cudaStream_t stream, KernelInfo *info);
-cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind, int block_threads,
+cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind,
                              const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out,
                              float *V_out, cudaStream_t stream, KernelInfo *info);
 
