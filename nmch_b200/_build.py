@@ -76,7 +76,7 @@ def build_cli(force: bool = False, verbose: bool = False):
             continue
         if force or _newer(exe, deps):
             cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), main, *api, "-o", exe,
-                   "-L", PKG, "-lnmch_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../nmch_b200"]
+                   "-L", PKG, "-lnmch_b200", "-pthread", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../nmch_b200"]
             if verbose:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)

@@ -45,17 +45,24 @@ double heston_call(double S0, double K, double v0, double r, double kappa, doubl
         const cd f = std::exp(C + D * v0 + iphi * lnS0);
         return (std::exp(-iphi * lnK) * f / iphi).real();
     };
-    const int panels = 4000;
-    const double h = 400.0 / panels;
+    // Panels of width 1/2 with 16 Gauss-Legendre nodes; the integrand decays exponentially, so stop once three
+    // consecutive panels contribute less than 1e-16 (at most 400 / 0.5 panels, as the fixed rule used before).
+    const double h = 0.5;
+    const int max_panels = 800;
     double I1 = 0.0, I2 = 0.0;
-    for (int p = 0; p < panels; ++p) {
+    int quiet = 0;
+    for (int p = 0; p < max_panels && quiet < 3; ++p) {
         const double mid = (p + 0.5) * h, half = 0.5 * h;
+        double d1 = 0.0, d2 = 0.0;
         for (int q = 0; q < 8; ++q)
             for (int s = -1; s <= 1; s += 2) {
                 const double phi = mid + s * half * gx[q];
-                I1 += gw[q] * half * integrand(phi, 1);
-                I2 += gw[q] * half * integrand(phi, 2);
+                d1 += gw[q] * half * integrand(phi, 1);
+                d2 += gw[q] * half * integrand(phi, 2);
             }
+        I1 += d1;
+        I2 += d2;
+        quiet = (std::fabs(d1) < 1e-16 && std::fabs(d2) < 1e-16) ? quiet + 1 : 0;
     }
     const double pi = 3.14159265358979323846;
     return S0 * (0.5 + I1 / pi) - K * std::exp(-r * T) * (0.5 + I2 / pi);
