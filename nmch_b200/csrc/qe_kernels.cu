@@ -70,14 +70,15 @@ qe_kernel(const __grid_constant__ QeLaunch L, const QePoint *__restrict__ pts, R
                 const float a = m * rcp_approx(1.0f + b2);
                 const float q = sqrt_approx(b2) + zv;
                 Vn = a * q * q;
-                const float den = 1.0f - 2.0f * pc.A * a;                       // > 0 for the usual rho < 0
+                const float den = fmaxf(1.0f - 2.0f * pc.A * a, 1e-6f);         // > 0 for the usual rho < 0; clamped so that
+                                                                                // a large positive rho cannot produce NaN
                 lnM = pc.A * b2 * a * rcp_approx(den) - 0.5f * __logf(den);
             } else {
                 // V' = 0 with probability p, else exponential with rate beta
                 const float p = (psi - 1.0f) * rcp_approx(psi + 1.0f);
                 const float beta = (1.0f - p) * rcp_approx(m);
                 Vn = (u <= p) ? 0.0f : __logf((1.0f - p) * rcp_approx(1.0f - u)) * rcp_approx(beta);
-                lnM = __logf(p + beta * (1.0f - p) * rcp_approx(beta - pc.A));
+                lnM = __logf(p + beta * (1.0f - p) * rcp_approx(fmaxf(beta - pc.A, 1e-6f)));
             }
             // ln S' = ln S + r dt - ln M - K3 V / 2 + K2 V' + sqrt(K3 V + K4 V') Z_s   (K0* with K1 V folded in)
             const float var = fmaf(pc.K3, V, pc.K4 * Vn);

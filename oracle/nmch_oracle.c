@@ -775,13 +775,13 @@ void orc_qe_run(const orc_params_t *p, uint64_t seed, uint64_t first_path, uint6
             float Vn, lnM;
             if (psi <= 1.5f) {
                 const float t = 2.0f / psi, b2 = t - 1.0f + sqrtf(t * (t - 1.0f)), a = m / (1.0f + b2);
-                const float q = sqrtf(b2) + zv, den = 1.0f - 2.0f * A * a;
+                const float q = sqrtf(b2) + zv, den = fmaxf(1.0f - 2.0f * A * a, 1e-6f);
                 Vn = a * q * q;
                 lnM = A * b2 * a / den - 0.5f * logf(den);
             } else {
                 const float pp = (psi - 1.0f) / (psi + 1.0f), beta = (1.0f - pp) / m;
                 Vn = (u <= pp) ? 0.0f : logf((1.0f - pp) / (1.0f - u)) / beta;
-                lnM = logf(pp + beta * (1.0f - pp) / (beta - A));
+                lnM = logf(pp + beta * (1.0f - pp) / fmaxf(beta - A, 1e-6f));
             }
             lnS += r_dt - lnM - 0.5f * K3 * V + K2 * Vn + sqrtf(fmaf(K3, V, K4 * Vn)) * zs;
             V = Vn;
