@@ -36,8 +36,13 @@ def _deps():
     return out
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into nmch_b200/libnmch_b200.so."""
+def build(force: bool = False, verbose: bool = False, only_if_missing: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into nmch_b200/libnmch_b200.so.
+
+    only_if_missing: never rebuild an existing library (what tests use: a snapshot copied to another machine may not
+    preserve modification times, and rebuilding a library that the running process has loaded is unsafe)."""
+    if only_if_missing and os.path.exists(LIB):
+        return LIB
     if force or _newer(LIB, _deps()):
         objs = []
         os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
@@ -57,9 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_cli(force: bool = False, verbose: bool = False):
+def build_cli(force: bool = False, verbose: bool = False, only_if_missing: bool = False):
     """Compile the C++ method API + the NMCH / exploration CLIs (host C++ over the C ABI)."""
-    build(force=force, verbose=verbose)
+    build(force=force, verbose=verbose, only_if_missing=only_if_missing)
     src_dir = os.path.join(ROOT, "src")
     if not os.path.isdir(src_dir):
         return []
@@ -73,6 +78,9 @@ def build_cli(force: bool = False, verbose: bool = False):
         exe = os.path.join(BIN, "NMCH" if name == "nmch" else "exploration")
         deps = api + [main, LIB]
         if not all(os.path.exists(d) for d in deps):
+            continue
+        if only_if_missing and os.path.exists(exe):
+            outs.append(exe)
             continue
         if force or _newer(exe, deps):
             cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), main, *api, "-o", exe,

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def lib():
-    _build.build()
+    _build.build(only_if_missing=True)
     return capi.load()
 
 

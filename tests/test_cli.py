@@ -15,7 +15,7 @@ EXPL = os.path.join(ROOT, "bin", "exploration")
 @pytest.fixture(scope="module", autouse=True)
 def _built():
     from nmch_b200 import _build
-    _build.build_cli()
+    _build.build_cli(only_if_missing=True)
     assert os.path.exists(NMCH) and os.path.exists(EXPL)
 
 

@@ -48,7 +48,7 @@ USER_CODE = textwrap.dedent(r"""
 @pytest.fixture(scope="module")
 def user_exe(tmp_path_factory):
     from nmch_b200 import _build
-    _build.build()
+    _build.build(only_if_missing=True)
     d = tmp_path_factory.mktemp("user")
     src = d / "user.cpp"
     src.write_text(USER_CODE)
