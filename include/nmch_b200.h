@@ -76,6 +76,10 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out);
 int nmch_engine_init(nmch_engine_t *e, unsigned long long seed);
 /* set_k / set_theta / set_sigma (NMCH.hpp:76-80): host fields only, effective at next compute */
 int nmch_engine_set_params(nmch_engine_t *e, float k, float theta, float sigma);
+/* Positions every path's stream as if `words` 32-bit draws had already been consumed (the `offset` argument of
+ * curand_init, which the reference always passes as 0, random.cu:9).  FE in the Philox modes only (a counter-based
+ * stream seeks for free); `words` must be even.  Other modes return NMCH_ERR_ARG. */
+int nmch_engine_seek(nmch_engine_t *e, unsigned long long words);
 /* compute() (NMCH_FE.cu:516-546): one pass over all local paths, streams continue across calls */
 int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out);
 /* Same pass, asynchronous: enqueued on `cuda_stream` (a cudaStream_t; NULL = the CUDA default stream),

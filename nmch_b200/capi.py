@@ -41,7 +41,7 @@ class NmchLaunchInfo(C.Structure):
 
 
 EXPORTS = [
-    "nmch_engine_create", "nmch_engine_init", "nmch_engine_set_params", "nmch_engine_compute",
+    "nmch_engine_create", "nmch_engine_init", "nmch_engine_set_params", "nmch_engine_seek", "nmch_engine_compute",
     "nmch_engine_compute_async", "nmch_engine_explore", "nmch_engine_explore_async",
     "nmch_engine_compute_paths", "nmch_engine_compute_strikes", "nmch_engine_compute_strikes_async",
     "nmch_engine_finalize", "nmch_engine_destroy", "nmch_engine_init_ms",
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     L.nmch_engine_create.argtypes = [C.POINTER(NmchParams), C.POINTER(vp)]
     L.nmch_engine_init.argtypes = [vp, C.c_ulonglong]
     L.nmch_engine_set_params.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    L.nmch_engine_seek.argtypes = [vp, C.c_ulonglong]
     L.nmch_engine_compute.argtypes = [vp, C.POINTER(NmchMoments)]
     L.nmch_engine_compute_async.argtypes = [vp, vp, vp]
     L.nmch_engine_explore.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.POINTER(NmchMoments)]

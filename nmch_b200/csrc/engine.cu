@@ -382,6 +382,17 @@ int nmch_engine_set_params(nmch_engine_t *e, float k, float theta, float sigma)
     return NMCH_OK;
 }
 
+int nmch_engine_seek(nmch_engine_t *e, unsigned long long words)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (e->p.method != NMCH_METHOD_FE || (e->p.rng != NMCH_RNG_PHILOX && e->p.rng != NMCH_RNG_PHILOX_COMPAT))
+        return fail(NMCH_ERR_ARG, "seek is available for FE in the Philox stream modes only");
+    if (words & 1ull) return fail(NMCH_ERR_ARG, "seek position must be an even number of 32-bit draws");
+    e->draw_offset = words;
+    return NMCH_OK;
+}
+
 int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out)
 {
     int rc = check_ready(e);

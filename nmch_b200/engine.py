@@ -66,6 +66,10 @@ class Engine:
     def set_params(self, k: float, theta: float, sigma: float) -> None:
         capi.check(self._lib.nmch_engine_set_params(self._h, k, theta, sigma))
 
+    def seek(self, words: int) -> None:
+        """Position the streams after `words` 32-bit draws per path (FE, Philox modes)."""
+        capi.check(self._lib.nmch_engine_seek(self._h, words))
+
     def compute(self) -> Moments:
         m = capi.NmchMoments()
         capi.check(self._lib.nmch_engine_compute(self._h, C.byref(m)))

@@ -520,9 +520,28 @@ static inline void fe_step(float *S, float *V, float gx, float gy, float r, floa
     *S = Sn; *V = Vn;
 }
 
+static void fe_run_impl(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed, uint64_t offset,
+                        uint64_t first_path, uint64_t n_paths, int calls,
+                        float *S_out, float *V_out, double *sum, double *sumsq, int threads);
+
 void orc_fe_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,
                 uint64_t first_path, uint64_t n_paths, int calls,
                 float *S_out, float *V_out, double *sum, double *sumsq, int threads)
+{
+    fe_run_impl(p, rng_kind, floor_kind, seed, 0, first_path, n_paths, calls, S_out, V_out, sum, sumsq, threads);
+}
+
+/* same, with the streams started at curand_init's `offset` (the reference always passes 0) */
+void orc_fe_run_at(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed, uint64_t offset,
+                   uint64_t first_path, uint64_t n_paths, int calls,
+                   float *S_out, float *V_out, double *sum, double *sumsq, int threads)
+{
+    fe_run_impl(p, rng_kind, floor_kind, seed, offset, first_path, n_paths, calls, S_out, V_out, sum, sumsq, threads);
+}
+
+static void fe_run_impl(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed, uint64_t offset,
+                        uint64_t first_path, uint64_t n_paths, int calls,
+                        float *S_out, float *V_out, double *sum, double *sumsq, int threads)
 {
     const float dt = p->T / p->N;                       /* NMCH.cu:9 */
     const float K = p->S_0;                             /* NMCH.cu:7 */
@@ -536,7 +555,7 @@ void orc_fe_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t se
 #endif
     for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
         orc_rng_t st;
-        orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, 0);   /* random.cu:8-9 */
+        orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, offset);   /* random.cu:8-9 (offset 0 there) */
         float St = 0, Vt = 0;
         for (int call = 0; call < calls; ++call) {
             St = p->S_0; Vt = p->v_0;

@@ -75,6 +75,11 @@ void orc_fe_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t se
                 uint64_t first_path, uint64_t n_paths, int calls,
                 float *S_out, float *V_out, double *sum, double *sumsq, int threads);
 
+/* same with curand_init's `offset` argument (u32 draws to skip; the reference always passes 0) */
+void orc_fe_run_at(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed, uint64_t offset,
+                   uint64_t first_path, uint64_t n_paths, int calls,
+                   float *S_out, float *V_out, double *sum, double *sumsq, int threads);
+
 /* The exploration sweep (src/NMCH/test/exploration.cu:71-88): per point set_k/theta/sigma + compute()
  * on continued streams.  sums has 2*n_points entries (raw sum, raw sum of squares per point). */
 void orc_fe_sweep(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,

@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
         L.orc_gamma.restype = C.c_float
         L.orc_fe_run.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                  C.c_int, f32p, f32p, f64p, f64p, C.c_int]
+        L.orc_fe_run_at.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                    C.c_int, f32p, f32p, f64p, f64p, C.c_int]
         L.orc_fe_sweep.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                    C.c_int, f32p, f32p, f32p, f64p, C.c_int]
         L.orc_em_run.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
@@ -174,6 +176,12 @@ def fe_run(p: Params, rng=RNG_XORWOW, floor=FLOOR_ABS, seed=1234, first_path=0, 
            want_paths=False, threads=0):
     """Reference FE kernel semantics (NMCH_FE.cu:145-175) for paths [first_path, first_path+n_paths)."""
     return _run(lib().orc_fe_run, p, (rng, floor, seed), first_path, n_paths, calls, want_paths, threads)
+
+
+def fe_run_at(p: Params, offset, rng=RNG_PHILOX, floor=FLOOR_ABS, seed=1234, first_path=0, n_paths=1024, calls=1,
+              want_paths=False, threads=0):
+    """fe_run with the streams started `offset` 32-bit draws in (curand_init's offset argument)."""
+    return _run(lib().orc_fe_run_at, p, (rng, floor, seed, offset), first_path, n_paths, calls, want_paths, threads)
 
 
 def fe_sweep(p: Params, k, theta, sigma, rng=RNG_XORWOW, floor=FLOOR_ABS, seed=1234, first_path=0, n_paths=1024,

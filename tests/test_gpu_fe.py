@@ -363,3 +363,32 @@ def test_explore_with_several_tiles_per_block_matches_sequential():
             s = e.compute()
             np.testing.assert_allclose([batched[i].sum_payoff, batched[i].sum_payoff_sq], [s.sum_payoff, s.sum_payoff_sq],
                                        rtol=1e-12)
+
+
+@pytest.mark.parametrize("rng,tol", [(0, 2e-3), (2, 2e-4)])
+@pytest.mark.parametrize("offset", [6, (1 << 34) - 12, (1 << 34) - 10, (1 << 40) + 2])
+def test_seek_and_block_counter_carry(rng, tol, offset):
+    # positions the Philox streams by hand; (2^34 - 12) words = 3 blocks before the LOW counter word wraps, so the
+    # 16-step run below crosses the carry into the high word (with and without a half-block start)
+    n, N = 2048, 16
+    with E.Engine(NTPB=512, NB=n // 512, N=N, rng=rng) as e:
+        e.init(1234)
+        e.seek(offset)
+        S, V, m = e.compute_paths()
+        S2, _, _ = e.compute_paths()                      # and the stream keeps going from there
+    ref = o.fe_run_at(o.Params(N=N), offset, rng=o.RNG_PHILOX, n_paths=n, calls=2, want_paths=True)
+    first = o.fe_run_at(o.Params(N=N), offset, rng=o.RNG_PHILOX, n_paths=n, want_paths=True)
+    np.testing.assert_allclose(S, first["S"], rtol=tol, atol=tol / 10)
+    np.testing.assert_allclose(S2, ref["S"], rtol=tol, atol=tol / 10)
+
+
+def test_seek_rejected_outside_philox_fe():
+    from nmch_b200 import capi
+    with E.Engine(NTPB=32, NB=4, N=10, rng=1) as e:
+        e.init(1)
+        with pytest.raises(capi.NmchError):
+            e.seek(4)
+    with E.Engine(NTPB=32, NB=4, N=10, rng=0) as e:
+        e.init(1)
+        with pytest.raises(capi.NmchError):
+            e.seek(3)
