@@ -182,12 +182,15 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                   int n_points, double *d_out, float *S_out, float *V_out)
 {
     const nmch_params_t &p = e->p;
-    const bool native = (p.rng == NMCH_RNG_PHILOX);
+    const bool exact = (p.rng == NMCH_RNG_PHILOX_COMPAT);        // Philox words, the reference's IEEE arithmetic
+    const bool native = (p.rng == NMCH_RNG_PHILOX) || exact;
     const bool own = (k == nullptr);
     if (p.method == NMCH_METHOD_FE) {
         FeLaunch L;
         if (native) {
-            const int P = pick_paths_per_thread(e, n_points), threads = e->threads;
+            int P = pick_paths_per_thread(e, n_points);
+            if (exact && P > 2) P = 2;
+            const int threads = e->threads;
             const unsigned long long tile = (unsigned long long)P * threads;
             const unsigned long long tiles = (e->n_local + tile - 1) / tile;
             // keep the per-point partial list short when many points share the launch
@@ -201,13 +204,14 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
             const FePoint *d_pts = nullptr;
             if (!own) {
                 std::vector<FePoint> pts(n_points);
-                for (int i = 0; i < n_points; ++i) pts[i] = fold_fe_point(p, k[i], theta[i], sigma[i]);
+                for (int i = 0; i < n_points; ++i)
+                    pts[i] = exact ? FePoint{k[i], theta[i], sigma[i], 0.0f} : fold_fe_point(p, k[i], theta[i], sigma[i]);
                 CU_TRY(cudaMemcpyAsync(e->d_points, pts.data(), pts.size() * sizeof(FePoint), cudaMemcpyHostToDevice, stream));
                 CU_TRY(cudaStreamSynchronize(stream));          // pts is a stack-lifetime staging buffer
                 d_pts = static_cast<const FePoint *>(e->d_points);
             }
             ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
-            CU_TRY(launch_fe_philox(L, p.floor, P, threads, d_pts, rb, S_out, V_out, stream, &e->kinfo));
+            CU_TRY(launch_fe_philox(L, p.floor, P, threads, exact, d_pts, rb, S_out, V_out, stream, &e->kinfo));
         } else {
             const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
             if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
@@ -226,7 +230,7 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
             if (p.rng == NMCH_RNG_MRG32K3A_COMPAT)
                 CU_TRY(launch_fe_compat_mrg(L, p.floor, d_pts, e->curand_states, rb, S_out, V_out, stream, &e->kinfo));
             else
-                CU_TRY(launch_fe_compat(L, p.rng, p.floor, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
+                CU_TRY(launch_fe_compat(L, p.floor, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
         }
         e->draw_offset += 2ull * (unsigned long long)p.N * (unsigned long long)n_points;
     } else if (p.method == NMCH_METHOD_EM) {
@@ -288,8 +292,9 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (p.first_path > n) return fail(NMCH_ERR_ARG, "first_path beyond n_paths");
     unsigned long long n_local = p.n_local ? p.n_local : n - p.first_path;
     if (n_local == 0 || p.first_path + n_local > n) return fail(NMCH_ERR_ARG, "empty or out-of-range shard");
-    if (p.rng == NMCH_RNG_PHILOX && !is_multiple_of(p.first_path, kMaxTilePaths))
-        return fail(NMCH_ERR_ARG, "native Philox mode needs first_path to be a multiple of 4096");
+    if ((p.rng == NMCH_RNG_PHILOX || (p.rng == NMCH_RNG_PHILOX_COMPAT && p.method == NMCH_METHOD_FE)) &&
+        !is_multiple_of(p.first_path, kMaxTilePaths))
+        return fail(NMCH_ERR_ARG, "the Philox FE modes need first_path to be a multiple of 4096");
     if (p.paths_per_thread != 0 && p.paths_per_thread != 1 && p.paths_per_thread != 2 && p.paths_per_thread != 4 &&
         p.paths_per_thread != 8)
         return fail(NMCH_ERR_ARG, "paths_per_thread must be 0 (auto), 1, 2, 4 or 8");

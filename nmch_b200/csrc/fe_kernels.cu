@@ -1,8 +1,9 @@
 // fe_kernels.cu -- forward-Euler Heston path kernels for sm_100a.
 //
 // Replaces FE_k1 / FE_k2 / FE_k2_philox / FE_k3 of the reference (src/NMCH/methods/NMCH_FE.cu:16-304)
-// with ONE native kernel (fe_philox_kernel) plus a validation kernel (fe_compat_kernel) that
-// reproduces the reference's cuRAND streams and IEEE arithmetic draw for draw.
+// with ONE native kernel (fe_philox_kernel; its EXACT instantiation is the cuRAND-Philox-compatible validation
+// mode) plus a validation kernel for the sequential XORWOW stream (fe_compat_kernel); both validation paths
+// reproduce the reference's cuRAND draws and IEEE arithmetic draw for draw.
 //
 // Native kernel, per path-step (see DESIGN.md §Kernels for the instruction budget):
 //   * half a Philox4x32-10 block (the block serves two steps; round keys sit in uniform registers, the
@@ -40,26 +41,42 @@ __device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, 
     V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
 }
 
+// One step in either arithmetic: the fused fast-math step above, or (EXACT) cuRAND's IEEE Box-Muller and the
+// reference's pinned update on the same two Philox words -- the Philox-compatible validation mode, which thereby
+// shares the counter hoisting, the tiling and the several-paths-per-thread structure of the product kernel.
+template <int FLOOR, bool EXACT>
+__device__ __forceinline__ void fe_step_any(float &S, float &V, uint32_t wa, uint32_t wb, const FeLaunch &L,
+                                            const FePoint &pc)
+{
+    if constexpr (EXACT) {
+        float gx, gy;
+        box_muller_compat(wa, wb, gx, gy);
+        // for EXACT launches the point record carries the raw (k, theta, sigma) in (va, vb, vs)
+        fe_step_compat<FLOOR>(S, V, gx, gy, L.r, pc.va, L.rho, pc.vb, pc.vs, L.dt, L.sqrt_dt, L.sqrt_rho);
+    } else {
+        fe_step_native<FLOOR>(S, V, wa, wb, L.crdt, L.zr, L.zc, pc);
+    }
+}
+
 // Resident blocks per SM the register allocator must leave room for (measured sweep, profiles/r01_fe_variants.txt):
 // 48 registers at P = 4 keeps 40 warps per SM in flight, which beats both more ILP and more occupancy.
-template <int P, int THREADS>
+template <int P, int THREADS, bool EXACT = false>
 struct FeOccupancy {
 #ifndef NMCHB_FE_WARPS_P4
 #define NMCHB_FE_WARPS_P4 40
 #endif
-    static constexpr int kWarpsTarget = (P <= 2) ? 48 : (P == 4 ? NMCHB_FE_WARPS_P4 : 24);
+    static constexpr int kWarpsTarget = EXACT ? 32 : ((P <= 2) ? 48 : (P == 4 ? NMCHB_FE_WARPS_P4 : 24));
     static constexpr int kMinBlocks = kWarpsTarget * 32 / THREADS;
 };
 
-template <int P, int FLOOR, int THREADS>
-__global__ void __launch_bounds__(THREADS, FeOccupancy<P, THREADS>::kMinBlocks)
+template <int P, int FLOOR, int THREADS, bool EXACT>
+__global__ void __launch_bounds__(THREADS, FeOccupancy<P, THREADS, EXACT>::kMinBlocks)
 fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ pts, ReduceBuffers rb,
                  float *__restrict__ S_out, float *__restrict__ V_out)
 {
     constexpr int TILE = P * THREADS;
     const int point = blockIdx.y;
-    const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
-    const float crdt = L.crdt, zr = L.zr, zc = L.zc;
+    const FePoint pc = (pts != nullptr) ? pts[point] : (EXACT ? FePoint{L.raw0.k, L.raw0.theta, L.raw0.sigma, 0.0f} : L.pt0);
 
     // stream position of this point: what `point` sequential compute() calls would have consumed
     const unsigned long long w0 = L.draw_offset + (unsigned long long)point * 2ull * (unsigned long long)L.N;
@@ -88,7 +105,7 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
-                fe_step_native<FLOOR>(S[j], V[j], w.z, w.w, crdt, zr, zc, pc);
+                fe_step_any<FLOOR, EXACT>(S[j], V[j], w.z, w.w, L, pc);
             }
             ++blk;
             --n;
@@ -111,8 +128,8 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
                     const U4 w = philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv[j], L.keys);
-                    fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
-                    fe_step_native<FLOOR>(S[j], V[j], w.z, w.w, crdt, zr, zc, pc);
+                    fe_step_any<FLOOR, EXACT>(S[j], V[j], w.x, w.y, L, pc);
+                    fe_step_any<FLOOR, EXACT>(S[j], V[j], w.z, w.w, L, pc);
                 }
             }
             blk += (unsigned long long)chunk;
@@ -122,7 +139,7 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
-                fe_step_native<FLOOR>(S[j], V[j], w.x, w.y, crdt, zr, zc, pc);
+                fe_step_any<FLOOR, EXACT>(S[j], V[j], w.x, w.y, L, pc);
             }
         }
         double2 acc = s_acc[threadIdx.x];
@@ -145,7 +162,7 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
     block_reduce_and_finish(total.x, total.y, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
 }
 
-template <int P, int FLOOR>
+template <int P, int FLOOR, bool EXACT>
 static cudaError_t launch_philox_t(const FeLaunch &L, int block_threads, const FePoint *d_pts,
                                    ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream,
                                    KernelInfo *info)
@@ -154,11 +171,11 @@ static cudaError_t launch_philox_t(const FeLaunch &L, int block_threads, const F
     cudaFuncAttributes attr{};
     cudaError_t err;
     if (block_threads == 128) {
-        fe_philox_kernel<P, FLOOR, 128><<<grid, 128, 0, stream>>>(L, d_pts, rb, S_out, V_out);
-        err = cudaFuncGetAttributes(&attr, fe_philox_kernel<P, FLOOR, 128>);
+        fe_philox_kernel<P, FLOOR, 128, EXACT><<<grid, 128, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_philox_kernel<P, FLOOR, 128, EXACT>);
     } else {
-        fe_philox_kernel<P, FLOOR, 256><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
-        err = cudaFuncGetAttributes(&attr, fe_philox_kernel<P, FLOOR, 256>);
+        fe_philox_kernel<P, FLOOR, 256, EXACT><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_philox_kernel<P, FLOOR, 256, EXACT>);
     }
     if (info) {
         info->grid_x = (int)grid.x;
@@ -172,19 +189,28 @@ static cudaError_t launch_philox_t(const FeLaunch &L, int block_threads, const F
     return lerr != cudaSuccess ? lerr : err;
 }
 
-cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int P, int block_threads, const FePoint *d_pts,
-                             ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
+cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int P, int block_threads, bool exact_math,
+                             const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream,
+                             KernelInfo *info)
 {
-#define NMCHB_DISPATCH(PP)                                                                                   \
-    case PP:                                                                                                 \
-        return floor_kind == kFloorAbs                                                                       \
-                   ? launch_philox_t<PP, kFloorAbs>(L, block_threads, d_pts, rb, S_out, V_out, stream, info) \
-                   : launch_philox_t<PP, kFloorPlus>(L, block_threads, d_pts, rb, S_out, V_out, stream, info);
+#define NMCHB_DISPATCH(PP, EX)                                                                                    \
+    case PP:                                                                                                      \
+        return floor_kind == kFloorAbs                                                                            \
+                   ? launch_philox_t<PP, kFloorAbs, EX>(L, block_threads, d_pts, rb, S_out, V_out, stream, info)  \
+                   : launch_philox_t<PP, kFloorPlus, EX>(L, block_threads, d_pts, rb, S_out, V_out, stream, info);
+    if (exact_math) {
+        switch (P) {
+            NMCHB_DISPATCH(1, true)
+            NMCHB_DISPATCH(2, true)
+        default:
+            return cudaErrorInvalidValue;
+        }
+    }
     switch (P) {
-        NMCHB_DISPATCH(1)
-        NMCHB_DISPATCH(2)
-        NMCHB_DISPATCH(4)
-        NMCHB_DISPATCH(8)
+        NMCHB_DISPATCH(1, false)
+        NMCHB_DISPATCH(2, false)
+        NMCHB_DISPATCH(4, false)
+        NMCHB_DISPATCH(8, false)
     default:
         return cudaErrorInvalidValue;
     }
@@ -206,31 +232,7 @@ struct CompatXorwow {
     }
 };
 
-struct CompatPhilox {                    // sequential view of the counter stream, always at an even position
-    unsigned long long pos;              // next u32 word
-    uint32_t path_lo, path_hi;
-    U4 cur;
-    __device__ __forceinline__ void start(unsigned long long p, uint32_t lo, uint32_t hi, const PhiloxKeys &K)
-    {
-        pos = p; path_lo = lo; path_hi = hi;
-        const unsigned long long b = pos >> 2;
-        cur = philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), path_lo, path_hi, K);
-    }
-    __device__ __forceinline__ void next2(uint32_t &a, uint32_t &b, const PhiloxKeys &K)
-    {
-        if (pos & 2ull) {
-            a = cur.z; b = cur.w;
-            pos += 2;
-            const unsigned long long blk = pos >> 2;
-            cur = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo, path_hi, K);
-        } else {
-            a = cur.x; b = cur.y;
-            pos += 2;
-        }
-    }
-};
-
-template <int RNG, int FLOOR>
+template <int FLOOR>
 __global__ void __launch_bounds__(256)
 fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict__ pts, XorwowState xs,
                  ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
@@ -238,28 +240,19 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
     CompatXorwow xw{};
-    CompatPhilox ph{};
     if (valid) {
-        if (RNG == kRngXorwowCompat) {
-            xw.d = xs.d[idx]; xw.v0 = xs.v0[idx]; xw.v1 = xs.v1[idx];
-            xw.v2 = xs.v2[idx]; xw.v3 = xs.v3[idx]; xw.v4 = xs.v4[idx];
-        } else {
-            const unsigned long long g = L.first_path + idx;
-            ph.start(L.draw_offset, (uint32_t)g, (uint32_t)(g >> 32), L.keys);
-        }
+        xw.d = xs.d[idx]; xw.v0 = xs.v0[idx]; xw.v1 = xs.v1[idx];
+        xw.v2 = xs.v2[idx]; xw.v3 = xs.v3[idx]; xw.v4 = xs.v4[idx];
     }
+    // the points of a sweep are walked inside the thread: the XORWOW stream is sequential, and this is exactly the
+    // reference's order (one compute() after the other on the state written back by the previous one)
     for (int point = 0; point < L.n_points; ++point) {
         const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
         float S = L.S0, V = L.v0;
         if (valid) {
             for (int n = 0; n < L.N; ++n) {
-                uint32_t a, b;
-                if (RNG == kRngXorwowCompat) {
-                    a = xw.next();
-                    b = xw.next();
-                } else {
-                    ph.next2(a, b, L.keys);
-                }
+                const uint32_t a = xw.next();
+                const uint32_t b = xw.next();
                 float gx, gy;
                 box_muller_compat(a, b, gx, gy);
                 fe_step_compat<FLOOR>(S, V, gx, gy, L.r, rp.k, L.rho, rp.theta, rp.sigma, L.dt, L.sqrt_dt,
@@ -277,35 +270,26 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
         block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x,
                                 L.blocks_per_point);
     }
-    if (valid && RNG == kRngXorwowCompat) {      // streams continue across compute() calls (NMCH_FE.cu:303)
+    if (valid) {                                 // streams continue across compute() calls (NMCH_FE.cu:303)
         xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;
         xs.v2[idx] = xw.v2; xs.v3[idx] = xw.v3; xs.v4[idx] = xw.v4;
     }
 }
 
-cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind,
-                             const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out, float *V_out,
-                             cudaStream_t stream, KernelInfo *info)
+cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,
+                             ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
 {
     const int threads = 256;                 // one path per thread; L.blocks_per_point is sized for this
     dim3 grid((unsigned)L.blocks_per_point, 1, 1);
     cudaFuncAttributes attr{};
     cudaError_t err = cudaSuccess;
-#define NMCHB_COMPAT(R, F)                                                                      \
-    do {                                                                                        \
-        fe_compat_kernel<R, F><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);   \
-        err = cudaFuncGetAttributes(&attr, fe_compat_kernel<R, F>);                             \
-    } while (0)
-    if (rng_kind == kRngXorwowCompat) {
-        if (floor_kind == kFloorAbs) NMCHB_COMPAT(kRngXorwowCompat, kFloorAbs);
-        else NMCHB_COMPAT(kRngXorwowCompat, kFloorPlus);
-    } else if (rng_kind == kRngPhiloxCompat) {
-        if (floor_kind == kFloorAbs) NMCHB_COMPAT(kRngPhiloxCompat, kFloorAbs);
-        else NMCHB_COMPAT(kRngPhiloxCompat, kFloorPlus);
+    if (floor_kind == kFloorAbs) {
+        fe_compat_kernel<kFloorAbs><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_compat_kernel<kFloorAbs>);
     } else {
-        return cudaErrorInvalidValue;
+        fe_compat_kernel<kFloorPlus><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_compat_kernel<kFloorPlus>);
     }
-#undef NMCHB_COMPAT
     if (info) {
         info->grid_x = (int)grid.x;
         info->grid_y = 1;

@@ -61,12 +61,13 @@ struct KernelInfo {
 };
 
 // fe_kernels.cu
+// exact_math: cuRAND's IEEE transforms + the reference's pinned update on the same Philox words (Philox-compat
+// mode); d_pts then holds raw (k, theta, sigma, 0) records instead of folded constants
 cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int paths_per_thread, int block_threads,
-                             const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out,
+                             bool exact_math, const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out,
                              cudaStream_t stream, KernelInfo *info);
-cudaError_t launch_fe_compat(const FeLaunch &L, int rng_kind, int floor_kind,
-                             const RawPoint *d_pts, XorwowState xs, ReduceBuffers rb, float *S_out,
-                             float *V_out, cudaStream_t stream, KernelInfo *info);
+cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,
+                             ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 
 // strike_kernels.cu: per-strike payoff / delta sums from terminal prices kept on the device
 cudaError_t launch_strike_moments(const float *d_S, unsigned long long n_local, const float *d_strikes, int n_strikes,

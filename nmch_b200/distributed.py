@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ALIGN = 4096      # native-mode tile alignment of first_path (include/nmch_b200.h)
+ALIGN = 4096      # tile alignment of first_path in the Philox FE modes (include/nmch_b200.h)
 
 
 def shard_bounds(n_paths: int, rank: int, world: int, align: int = ALIGN):
