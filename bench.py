@@ -146,10 +146,25 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3):
             units = n * N if method == "fe" else n
             out[rng] = {"value": units / (ms * 1e-3), "exec_ms": ms, "init_ms": rows[0]["init_ms"],
                         "E": rows[-1]["E"], "E2": rows[-1]["E2"]}
+            # same seed, same calls through OUR draw-compatible stream mode: identical results, our timing
+            try:
+                from nmch_b200 import engine as E
+                mode = E.RNG_XORWOW_COMPAT if rng == "xorwow" else E.RNG_PHILOX_COMPAT
+                with E.Engine(NTPB=512, NB=n // 512, N=N, method=E.METHOD_FE if method == "fe" else E.METHOD_EM, rng=mode,
+                              **README) as eng:
+                    eng.init(1234)
+                    eng.compute()
+                    ours = [eng.compute() for _ in range(repeat)]
+                rel = max(abs(o_.mean - r_["E"]) / abs(r_["E"]) for o_, r_ in zip(ours, rows))
+                best = min(o_.exec_ms for o_ in ours)
+                out[rng]["ours_same_draws"] = {"value": units / (best * 1e-3), "exec_ms": best, "max_rel_diff_E": rel}
+            except Exception as ex:  # noqa: BLE001
+                out[rng]["ours_same_draws"] = {"error": str(ex)[:200]}
         except Exception as ex:  # noqa: BLE001
             out[rng] = {"error": str(ex)[:200]}
     out["what"] = (f"reference NMCH_{method.upper()}_K3_MM<rng> (unmodified sources, -O3 -arch=sm_100), 512 x {n // 512} "
-                   f"paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); unit as `unit`")
+                   f"paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); unit as `unit`; ours_same_draws = "
+                   "this engine in the draw-compatible mode for that tag, same seed and calls (relative difference of E[X])")
     return out
 
 
@@ -300,8 +315,14 @@ def main():
         mean = float(result[0]) / n_total
         var = float(result[1]) / n_total - mean * mean
         f_hz = (ck["sm_mhz"] or 1965) * 1e6
-        peak = info["sm_count"] * f_hz * ISSUE_PER_CLK_PER_SM
         per_gpu = value / world
+        if args.method == "fe":
+            peak = info["sm_count"] * f_hz * ISSUE_PER_CLK_PER_SM
+        else:
+            # EM has no budget in SURVEY §8d.  Cost model measured for the FE kernel: an IMAD.WIDE.U32
+            # costs ~5.2 FMA-pipe cycles, an FP32 op ~1; one EM trial has 18 + 24 of them and a step takes 1.045 trials
+            cycles_per_warp_step = (18 * 5.2 + 24) * 1.045
+            peak = info["sm_count"] * f_hz * 4 * 32 / (cycles_per_warp_step * N)
         traffic = None
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj):
@@ -321,8 +342,10 @@ def main():
                          "traffic": traffic,
                          "model": "SURVEY.md §8d: SMs x f x min(128/42 issue, 16/5 MUFU) path-steps/s; f = median SM clock "
                                   "sampled during the timed region; per-GPU achieved" if args.method == "fe" else
-                                  "EM has no fixed instruction budget (data-dependent samplers); FE model shown for scale",
-                         "peak_at_max_clock": info["sm_count"] * (ck["sm_max_mhz"] or 1965) * 1e6 * ISSUE_PER_CLK_PER_SM,
+                                  "no SURVEY budget for EM: FMA-pipe cost model of DESIGN.md §4.1/4.3 -- (18 IMAD.WIDE x 5.2 + 24 FP32) "
+                                  "cycles per warp-trial x 1.045 trials per step x N steps; paths/s per GPU",
+                         "peak_at_max_clock": (info["sm_count"] * (ck["sm_max_mhz"] or 1965) * 1e6 * ISSUE_PER_CLK_PER_SM
+                                               if args.method == "fe" else None),
                          "mix_bound_peak": (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP
                                             if args.method == "fe" else None),
                          "mix_bound_frac": (per_gpu / (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP)
