@@ -145,7 +145,12 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         int step = 0;
         bool have_np = false;
         float np = 0.0f;
+        // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive), so
+        // the loop terminates; the cap on the Poisson-mixture path is a belt against a hang: a path that exhausts it
+        // ends early and poisons the sum with NaN instead of stalling the GPU.  (The split path is not taxed with it.)
+        const uint32_t max_blocks = 64u * (uint32_t)L.N + 4096u;
         while (step < L.N) {
+            if (MIXED && !pc.fast && blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
             const U4 w = next_block(blk++);
             float gsum;
             bool accept;
@@ -455,6 +460,15 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
     return pt;
 }
 
+static bool em_point_finite(const EmPoint &pt)
+{
+    const float v[] = {pt.scale, pt.two_lc, pt.lc, pt.d, pt.a, pt.mt_d, pt.mt_c, pt.inv_a, pt.f_c, pt.f_h, pt.f_dl,
+                       pt.f_g2, pt.f_scale, pt.k, pt.ktheta_T, pt.inv_sigma};
+    for (float x : v)
+        if (!std::isfinite(x)) return false;
+    return pt.scale > 0.0f && pt.lc > 0.0f;
+}
+
 
 template <typename State>
 static int curand_states_init(nmch_engine *e)
@@ -494,6 +508,8 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
         for (int i = 0; i < n_points; ++i) {
             pts[i] = own ? fold_em_point(p, p.k, p.theta, p.sigma) : fold_em_point(p, k[i], theta[i], sigma[i]);
             all_fast = all_fast && pts[i].fast;
+            if (!em_point_finite(pts[i]))
+                return engine_fail(NMCH_ERR_ARG, "EM: parameters out of the representable range (k dt or sigma^2 too small / large)");
         }
         int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(EmPoint));
         if (rc) return rc;

@@ -176,6 +176,15 @@ int ensure_sv(nmch_engine *e, size_t count)
     return NMCH_OK;
 }
 
+// The rejection samplers of EM and the moment matching of QE need k, sigma > 0 and finite, non-negative levels.
+static int validate_point(int method, float k, float theta, float sigma, float v0)
+{
+    if (method == NMCH_METHOD_FE) return NMCH_OK;                       // the Euler step is total: any floats go through
+    const bool ok = std::isfinite(k) && std::isfinite(theta) && std::isfinite(sigma) && k > 0.0f && sigma > 0.0f &&
+                    theta >= 0.0f && v0 >= 0.0f;
+    return ok ? NMCH_OK : fail(NMCH_ERR_ARG, "EM / QE need k > 0, sigma > 0, theta >= 0, v_0 >= 0 (finite)");
+}
+
 // One launch over n_points parameter points.  k/theta/sigma are HOST arrays (nullptr => the engine's own
 // current parameters, n_points == 1).  Raw sums go to d_out (device-accessible, 2*n_points doubles).
 int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const float *theta, const float *sigma,
@@ -185,6 +194,11 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
     const bool exact = (p.rng == NMCH_RNG_PHILOX_COMPAT);        // Philox words, the reference's IEEE arithmetic
     const bool native = (p.rng == NMCH_RNG_PHILOX) || exact;
     const bool own = (k == nullptr);
+    for (int i = 0; i < n_points; ++i) {
+        const int rc = own ? validate_point(p.method, p.k, p.theta, p.sigma, p.v_0)
+                           : validate_point(p.method, k[i], theta[i], sigma[i], p.v_0);
+        if (rc) return rc;
+    }
     if (p.method == NMCH_METHOD_FE) {
         FeLaunch L;
         if (native) {

@@ -200,3 +200,21 @@ def test_full_size_properties_2_pow_22():
             halves.append(e.compute())
     assert abs(halves[0].sum_payoff + halves[1].sum_payoff - a.sum_payoff) < 1e-10 * n   # shards add up
     assert abs(a.mean - o.heston_call()) < 3 * a.std_error                               # unbiased at 8.6e-5
+
+
+def test_degenerate_parameters_are_rejected_not_hung():
+    from nmch_b200 import capi
+    for kw in (dict(sigma=0.0), dict(k=0.0), dict(k=-1.0), dict(theta=float("nan")), dict(v_0=-0.1)):
+        for method in (E.METHOD_EM, E.METHOD_QE):
+            with E.Engine(NTPB=32, NB=4, N=10, method=method, **kw) as e:
+                e.init(1)
+                with pytest.raises(capi.NmchError) as ei:
+                    e.compute()
+                assert ei.value.status == capi.ERR_ARG
+    with em_engine(128, 10) as e:                     # setters are validated at the next compute, like the reference's
+        e.init(1)
+        e.set_params(0.5, 0.1, 0.0)
+        with pytest.raises(capi.NmchError):
+            e.compute()
+        e.set_params(0.5, 0.1, 0.3)
+        assert e.compute().n_paths == 128
