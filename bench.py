@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--log2-paths", type=int, default=None, help="paths per GPU (default 24 for FE, 22 for EM)")
     ap.add_argument("--N", type=int, default=1000)
     ap.add_argument("--floor", default="abs", choices=["abs", "plus"])
+    ap.add_argument("--rng", default="philox", choices=["philox", "dense"],
+                    help="philox: word-compatible native stream (default); dense: opt-in 3-steps-per-block FE stream")
     ap.add_argument("--paths-per-thread", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,7 +201,7 @@ def main():
     workload = (f"BASELINE configs[1]: FE Euler |.| floor, README params, N={N}, 2^{log2_paths} paths per GPU, seed 1234"
                 if args.method == "fe" else
                 f"BASELINE configs[2]: EM exact scheme, README params, N={N}, 2^{log2_paths} paths per GPU, seed 1234")
-    config = {"workload": workload, "method": args.method, "floor": args.floor, "n_steps": N,
+    config = {"workload": workload, "method": args.method, "floor": args.floor, "rng": args.rng, "n_steps": N,
               "paths_per_gpu": n_per_gpu, "global_paths": n_per_gpu * world, "parallelism": f"paths sharded x{world}",
               "l2": "n/a: the kernel has no HBM-resident inputs (11 scalars by value), state lives in registers"}
 
@@ -252,7 +254,8 @@ def main():
     torch.cuda.set_stream(stream)
     sh = ShardedEngine(rank=rank, world=world, device=local_rank, NTPB=512, NB=(n_per_gpu * world) // 512, N=N,
                        method=E.METHOD_FE if args.method == "fe" else E.METHOD_EM,
-                       floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, rng=E.RNG_PHILOX,
+                       floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS,
+                       rng=E.RNG_PHILOX_DENSE if (args.rng == "dense" and args.method == "fe") else E.RNG_PHILOX,
                        paths_per_thread=args.paths_per_thread, block_threads=args.block_threads, **README)
     sh.init(1234)
     eng = sh.engine
@@ -354,6 +357,19 @@ def main():
             "result": {"E[X]": mean, "var": var, "std_error": (var / n_total) ** 0.5,
                        "heston_semi_analytic": 0.1197325094 if args.method in ("fe", "em") else None},
         }
+        if world == 1 and args.method == "fe" and args.rng == "philox":
+            try:                                  # the opt-in dense-draw stream, same workload, for the record
+                with E.Engine(NTPB=512, NB=n_per_gpu // 512, N=N, rng=E.RNG_PHILOX_DENSE, device=local_rank,
+                              floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, **README) as de:
+                    de.init(1234)
+                    de.compute()
+                    dms = min(de.compute().exec_ms for _ in range(3))
+                dval = units_per_gpu_step / (dms * 1e-3)
+                line["dense_mode"] = {"value": dval, "unit": unit, "ms_per_step": dms, "roofline_frac": dval / peak,
+                                      "note": "NMCH_RNG_PHILOX_DENSE: three (22-bit, 20-bit) draws per Philox block; "
+                                              "statistically equivalent, not cuRAND-word-compatible; bench.py --rng dense"}
+            except Exception as ex:  # noqa: BLE001
+                line["dense_mode"] = {"error": str(ex)[:200]}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.method, N, budget_s=args.cpu_budget_s or 12.0)
         if not args.no_reference_cuda and world == 1:

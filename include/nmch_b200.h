@@ -41,9 +41,13 @@ typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
  *   XORWOW_COMPAT  curandStateXORWOW_t-compatible: same integer stream, same IEEE transforms and FMA
  *                  contraction as the reference's CUDA build
  *   PHILOX_COMPAT  curandStatePhilox4_32_10_t-compatible (reference CLI default, nmch.cu:119,130)
- *   MRG32K3A_COMPAT curandStateMRG32k3a_t-compatible (the third tag the reference instantiates, NMCH.cu:31) */
+ *   MRG32K3A_COMPAT curandStateMRG32k3a_t-compatible (the third tag the reference instantiates, NMCH.cu:31)
+ *   PHILOX_DENSE   opt-in FE throughput mode: the same Philox4x32-10 blocks cut into THREE (22-bit radius, 20-bit
+ *                  angle) draws instead of two word pairs, i.e. a third fewer generator multiplies per step.  Statistically
+ *                  equivalent, NOT word-compatible with cuRAND's per-step layout (checked against a restatement of its
+ *                  own mapping and against the semi-analytic price) */
 typedef enum { NMCH_RNG_PHILOX = 0, NMCH_RNG_XORWOW_COMPAT = 1, NMCH_RNG_PHILOX_COMPAT = 2,
-               NMCH_RNG_MRG32K3A_COMPAT = 3 } nmch_rng;
+               NMCH_RNG_MRG32K3A_COMPAT = 3, NMCH_RNG_PHILOX_DENSE = 4 } nmch_rng;
 
 /* Replaces the constructor arguments of nmch::methods::NMCH (include/NMCH/methods/NMCH.hpp:42,
  * src/NMCH/methods/NMCH.cu:6-10).  Zero in an "auto" field selects the default. */

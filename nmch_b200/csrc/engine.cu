@@ -192,7 +192,8 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
 {
     const nmch_params_t &p = e->p;
     const bool exact = (p.rng == NMCH_RNG_PHILOX_COMPAT);        // Philox words, the reference's IEEE arithmetic
-    const bool native = (p.rng == NMCH_RNG_PHILOX) || exact;
+    const bool dense = (p.rng == NMCH_RNG_PHILOX_DENSE);         // three steps per Philox block
+    const bool native = (p.rng == NMCH_RNG_PHILOX) || exact || dense;
     const bool own = (k == nullptr);
     for (int i = 0; i < n_points; ++i) {
         const int rc = own ? validate_point(p.method, p.k, p.theta, p.sigma, p.v_0)
@@ -204,7 +205,8 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
         if (native) {
             int P = pick_paths_per_thread(e, n_points);
             if (exact && P > 2) P = 2;
-            const int threads = e->threads;
+            if (dense && P > 4) P = 4;
+            const int threads = dense ? 128 : e->threads;
             const unsigned long long tile = (unsigned long long)P * threads;
             const unsigned long long tiles = (e->n_local + tile - 1) / tile;
             // keep the per-point partial list short when many points share the launch
@@ -225,7 +227,10 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                 d_pts = static_cast<const FePoint *>(e->d_points);
             }
             ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
-            CU_TRY(launch_fe_philox(L, p.floor, P, threads, exact, d_pts, rb, S_out, V_out, stream, &e->kinfo));
+            if (dense)
+                CU_TRY(launch_fe_dense(L, p.floor, P, d_pts, rb, S_out, V_out, stream, &e->kinfo));
+            else
+                CU_TRY(launch_fe_philox(L, p.floor, P, threads, exact, d_pts, rb, S_out, V_out, stream, &e->kinfo));
         } else {
             const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
             if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
@@ -297,7 +302,9 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (p.method == NMCH_METHOD_QE && p.rng != NMCH_RNG_PHILOX)
         return fail(NMCH_ERR_ARG, "the QE scheme has no reference counterpart to be draw-compatible with: use rng = PHILOX");
     if (p.floor != NMCH_FLOOR_ABS && p.floor != NMCH_FLOOR_PLUS) return fail(NMCH_ERR_ARG, "unknown floor");
-    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_MRG32K3A_COMPAT) return fail(NMCH_ERR_ARG, "unknown rng mode");
+    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_PHILOX_DENSE) return fail(NMCH_ERR_ARG, "unknown rng mode");
+    if (p.rng == NMCH_RNG_PHILOX_DENSE && p.method != NMCH_METHOD_FE)
+        return fail(NMCH_ERR_ARG, "PHILOX_DENSE is an FE stream mode");
     unsigned long long n = p.n_paths;
     if (n == 0) {
         if (p.NTPB <= 0 || p.NB <= 0) return fail(NMCH_ERR_ARG, "NTPB and NB must be positive");
@@ -306,7 +313,8 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (p.first_path > n) return fail(NMCH_ERR_ARG, "first_path beyond n_paths");
     unsigned long long n_local = p.n_local ? p.n_local : n - p.first_path;
     if (n_local == 0 || p.first_path + n_local > n) return fail(NMCH_ERR_ARG, "empty or out-of-range shard");
-    if ((p.rng == NMCH_RNG_PHILOX || (p.rng == NMCH_RNG_PHILOX_COMPAT && p.method == NMCH_METHOD_FE)) &&
+    if ((p.rng == NMCH_RNG_PHILOX || p.rng == NMCH_RNG_PHILOX_DENSE ||
+         (p.rng == NMCH_RNG_PHILOX_COMPAT && p.method == NMCH_METHOD_FE)) &&
         !is_multiple_of(p.first_path, kMaxTilePaths))
         return fail(NMCH_ERR_ARG, "the Philox FE modes need first_path to be a multiple of 4096");
     if (p.paths_per_thread != 0 && p.paths_per_thread != 1 && p.paths_per_thread != 2 && p.paths_per_thread != 4 &&
@@ -405,7 +413,8 @@ int nmch_engine_seek(nmch_engine_t *e, unsigned long long words)
 {
     int rc = check_ready(e);
     if (rc) return rc;
-    if (e->p.method != NMCH_METHOD_FE || (e->p.rng != NMCH_RNG_PHILOX && e->p.rng != NMCH_RNG_PHILOX_COMPAT))
+    if (e->p.method != NMCH_METHOD_FE || (e->p.rng != NMCH_RNG_PHILOX && e->p.rng != NMCH_RNG_PHILOX_COMPAT &&
+                                          e->p.rng != NMCH_RNG_PHILOX_DENSE))
         return fail(NMCH_ERR_ARG, "seek is available for FE in the Philox stream modes only");
     if (words & 1ull) return fail(NMCH_ERR_ARG, "seek position must be an even number of 32-bit draws");
     e->draw_offset = words;

@@ -162,6 +162,173 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
     block_reduce_and_finish(total.x, total.y, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
 }
 
+// ------------------------------------------------------------------------------------------
+// dense-draw variant (opt-in stream mode NMCH_RNG_PHILOX_DENSE): THREE steps per Philox block.
+// The product kernel is bound by the 32x32->64 multiplies of Philox; this variant spends a third
+// fewer of them by cutting each 128-bit block into three (22-bit radius, 20-bit angle) field pairs instead of two
+// (32, 32) word pairs.  The price: a (path, step) no longer consumes the words cuRAND's layout assigns to it, so this
+// mode is checked against a restatement of ITS mapping and statistically, not against the reference's Philox stream.
+//   step A: radius = x[31:10]              angle = x[9:0]  : y[31:22]
+//   step B: radius = y[21:0]               angle = z[31:12]
+//   step C: radius = z[11:0] : w[31:22]    angle = w[21:2]                 (2 bits unused)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dense_fields(const U4 &w, int phase, float &f1, float &f2)
+{
+    uint32_t r, a;                                   // mantissas: radius field << 1, angle field << 3
+    if (phase == 0) {
+        r = (w.x >> 9) & 0x7ffffeu;
+        a = __funnelshift_r(w.y, w.x, 19) & 0x7ffff8u;
+    } else if (phase == 1) {
+        r = (w.y << 1) & 0x7ffffeu;
+        a = (w.z >> 9) & 0x7ffff8u;
+    } else {
+        r = __funnelshift_r(w.w, w.z, 21) & 0x7ffffeu;
+        a = (w.w << 1) & 0x7ffff8u;
+    }
+    f1 = __uint_as_float(r | 0x3f800000u);
+    f2 = __uint_as_float(a | 0x3f800000u);
+}
+
+template <int FLOOR>
+__device__ __forceinline__ void fe_step_dense(float &S, float &V, const U4 &w, int phase, const FeLaunch &L,
+                                              const FePoint &pc)
+{
+    float f1, f2;
+    dense_fields(w, phase, f1, f2);
+    const float u = f1 - 0.99999988f;                 // (k22 + 0.5) * 2^-22, in (0,1): exact
+    const float l2 = lg2_approx(u);
+    const float q = sqrt_approx(-(V * l2));
+    const float ang = f2 * 6.2831855f;
+    const float gs = q * sin_approx(ang);
+    const float gc = q * cos_approx(ang);
+    float m = fmaf(gs, L.zr, L.crdt);
+    m = fmaf(gc, L.zc, m);
+    S *= m;
+    float vn = fmaf(V, pc.va, pc.vb);
+    vn = fmaf(gs, pc.vs, vn);
+    V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
+}
+
+template <int P, int FLOOR, int THREADS>
+__global__ void __launch_bounds__(THREADS, FeOccupancy<P, THREADS>::kMinBlocks)
+fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ pts, ReduceBuffers rb,
+                float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    constexpr int TILE = P * THREADS;
+    const int point = blockIdx.y;
+    const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
+    // stream position in STEPS: draw_offset counts two logical draws per step, like the other modes
+    const unsigned long long s0 = (L.draw_offset >> 1) + (unsigned long long)point * (unsigned long long)L.N;
+    const int phase0 = (int)(s0 % 3ull);
+
+    __shared__ double2 s_acc[THREADS];
+    s_acc[threadIdx.x] = make_double2(0.0, 0.0);
+    for (int t = 0; t < L.tiles_per_block; ++t) {
+        const unsigned long long tile = (unsigned long long)blockIdx.x * L.tiles_per_block + t;
+        const unsigned long long local0 = tile * TILE;
+        if (local0 >= L.n_local) break;
+        const unsigned long long g0 = L.first_path + local0;
+        const uint32_t path_hi = (uint32_t)(g0 >> 32);
+        const uint32_t path_lo0 = (uint32_t)g0 + threadIdx.x;
+        float S[P], V[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            S[j] = L.S0;
+            V[j] = L.v0;
+        }
+        unsigned long long blk = s0 / 3ull;
+        int n = L.N;
+        if (phase0 != 0 && n > 0) {                               // finish the block a previous call left half used
+            const int cnt = min(3 - phase0, n);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
+                for (int ph = phase0; ph < phase0 + cnt; ++ph) fe_step_dense<FLOOR>(S[j], V[j], w, ph, L, pc);
+            }
+            ++blk;
+            n -= cnt;
+        }
+        int triples = n / 3;
+        while (triples > 0) {                                     // same counter split as the product kernel
+            const uint32_t blk_hi = (uint32_t)(blk >> 32);
+            const uint32_t blk_lo = (uint32_t)blk;
+            const unsigned long long room = 0x100000000ull - (unsigned long long)blk_lo;
+            const int chunk = ((unsigned long long)triples < room) ? triples : (int)room;
+            PhiloxPathInv inv[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) inv[j] = philox_path_invariants(blk_hi, path_lo0 + j * THREADS, L.keys);
+#pragma unroll 1
+            for (int it = 0; it < chunk; ++it) {
+                const unsigned long long s = (unsigned long long)kPhiloxM0 * (blk_lo + (uint32_t)it);
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const U4 w = philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv[j], L.keys);
+                    fe_step_dense<FLOOR>(S[j], V[j], w, 0, L, pc);
+                    fe_step_dense<FLOOR>(S[j], V[j], w, 1, L, pc);
+                    fe_step_dense<FLOOR>(S[j], V[j], w, 2, L, pc);
+                }
+            }
+            blk += (unsigned long long)chunk;
+            triples -= chunk;
+        }
+        const int rest = n % 3;
+        if (rest > 0) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
+                for (int ph = 0; ph < rest; ++ph) fe_step_dense<FLOOR>(S[j], V[j], w, ph, L, pc);
+            }
+        }
+        double2 acc = s_acc[threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const unsigned long long idx = local0 + (unsigned long long)(j * THREADS) + threadIdx.x;
+            if (idx < L.n_local) {
+                const double pay = (double)fmaxf(0.0f, S[j] - L.K);
+                acc.x += pay;
+                acc.y += pay * pay;
+                if (S_out != nullptr && point == L.n_points - 1) {
+                    S_out[idx] = S[j];
+                    V_out[idx] = V[j];
+                }
+            }
+        }
+        s_acc[threadIdx.x] = acc;
+    }
+    const double2 total = s_acc[threadIdx.x];
+    block_reduce_and_finish(total.x, total.y, rb.partials, rb.tickets, rb.out, point, blockIdx.x, L.blocks_per_point);
+}
+
+template <int P, int FLOOR>
+static cudaError_t launch_dense_t(const FeLaunch &L, const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out,
+                                  cudaStream_t stream, KernelInfo *info)
+{
+    dim3 grid((unsigned)L.blocks_per_point, (unsigned)L.n_points, 1);
+    fe_dense_kernel<P, FLOOR, 128><<<grid, 128, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+    cudaFuncAttributes attr{};
+    const cudaError_t err = cudaFuncGetAttributes(&attr, fe_dense_kernel<P, FLOOR, 128>);
+    if (info)
+        *info = KernelInfo{(int)grid.x, (int)grid.y, 128, P, attr.numRegs,
+                           (int)(sizeof(FeLaunch) + sizeof(const FePoint *) + sizeof(ReduceBuffers) + 2 * sizeof(float *))};
+    const cudaError_t lerr = cudaGetLastError();
+    return lerr != cudaSuccess ? lerr : err;
+}
+
+cudaError_t launch_fe_dense(const FeLaunch &L, int floor_kind, int P, const FePoint *d_pts, ReduceBuffers rb,
+                            float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
+{
+    const bool abs_floor = floor_kind == kFloorAbs;
+    switch (P) {
+    case 1: return abs_floor ? launch_dense_t<1, kFloorAbs>(L, d_pts, rb, S_out, V_out, stream, info)
+                             : launch_dense_t<1, kFloorPlus>(L, d_pts, rb, S_out, V_out, stream, info);
+    case 2: return abs_floor ? launch_dense_t<2, kFloorAbs>(L, d_pts, rb, S_out, V_out, stream, info)
+                             : launch_dense_t<2, kFloorPlus>(L, d_pts, rb, S_out, V_out, stream, info);
+    case 4: return abs_floor ? launch_dense_t<4, kFloorAbs>(L, d_pts, rb, S_out, V_out, stream, info)
+                             : launch_dense_t<4, kFloorPlus>(L, d_pts, rb, S_out, V_out, stream, info);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int P, int FLOOR, bool EXACT>
 static cudaError_t launch_philox_t(const FeLaunch &L, int block_threads, const FePoint *d_pts,
                                    ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream,

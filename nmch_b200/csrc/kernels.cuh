@@ -8,7 +8,7 @@
 namespace nmchb {
 
 constexpr int kFloorAbs = 0, kFloorPlus = 1;
-constexpr int kRngPhilox = 0, kRngXorwowCompat = 1, kRngPhiloxCompat = 2;
+constexpr int kRngPhilox = 0, kRngXorwowCompat = 1, kRngPhiloxCompat = 2, kRngMrgCompat = 3, kRngPhiloxDense = 4;
 constexpr int kMaxTilePaths = 4096;     // native mode: first_path % kMaxTilePaths == 0 (no carry inside a tile)
 
 // Per-point constants of the native FE kernel, folded on the host (fold_fe_point):
@@ -66,6 +66,9 @@ struct KernelInfo {
 cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int paths_per_thread, int block_threads,
                              bool exact_math, const FePoint *d_pts, ReduceBuffers rb, float *S_out, float *V_out,
                              cudaStream_t stream, KernelInfo *info);
+// dense-draw variant: three steps per Philox block (NMCH_RNG_PHILOX_DENSE); block size 128, P in {1, 2, 4}
+cudaError_t launch_fe_dense(const FeLaunch &L, int floor_kind, int paths_per_thread, const FePoint *d_pts, ReduceBuffers rb,
+                            float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,
                              ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 

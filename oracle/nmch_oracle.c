@@ -254,6 +254,12 @@ void orc_rng_init(orc_rng_t *s, int kind, uint64_t seed, uint64_t subsequence, u
         xorwow_init(s, seed, subsequence, offset);
     } else if (kind == ORC_RNG_MRG32K3A) {
         mrg_init(s, seed, subsequence, offset);
+    } else if (kind == ORC_RNG_PHILOX_DENSE) {
+        s->key[0] = (uint32_t)seed;
+        s->key[1] = (uint32_t)(seed >> 32);
+        s->ctr[2] = (uint32_t)subsequence;
+        s->ctr[3] = (uint32_t)(subsequence >> 32);
+        s->dense_step = offset / 2;                          /* two logical draws per step */
     } else {
         /* curand_init for Philox, curand_kernel.h:1022-1037, skipahead :971-981 */
         s->key[0] = (uint32_t)seed;
@@ -309,6 +315,24 @@ static inline void box_muller(uint32_t x, uint32_t y, float *gx, float *gy)
 
 void orc_normal2(orc_rng_t *s, float *gx, float *gy)
 {   /* curand_normal2, curand_normal.h:405-408, 424-427 */
+    if (s->kind == ORC_RNG_PHILOX_DENSE) {                   /* restates dense_fields + fe_step_dense of fe_kernels.cu */
+        const uint64_t blk = s->dense_step / 3;
+        const int phase = (int)(s->dense_step % 3);
+        const uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), s->ctr[2], s->ctr[3]};
+        uint32_t w[4];
+        orc_philox4x32_10(ctr, s->key, w);
+        uint32_t k22, k20;
+        if (phase == 0) { k22 = w[0] >> 10; k20 = ((w[0] & 0x3ffu) << 10) | (w[1] >> 22); }
+        else if (phase == 1) { k22 = w[1] & 0x3fffffu; k20 = w[2] >> 12; }
+        else { k22 = ((w[2] & 0xfffu) << 10) | (w[3] >> 22); k20 = (w[3] >> 2) & 0xfffffu; }
+        const float u = ((float)k22 + 0.5f) * 2.3841858e-07f;            /* 2^-22 */
+        const float ang = (1.0f + (float)k20 * 9.5367432e-07f) * 6.2831855f;  /* 2^-20 */
+        const float r = sqrtf(-2.0f * logf(u));
+        *gx = sinf(ang) * r;
+        *gy = cosf(ang) * r;
+        s->dense_step++;
+        return;
+    }
     if (s->kind == ORC_RNG_MRG32K3A) {                       /* curand_box_muller_mrg, curand_normal.h:89-108 */
         const float x = orc_uniform(s);
         const float y = orc_uniform(s) * 6.2831855f;

@@ -26,7 +26,10 @@ extern "C" {
 #endif
 
 /* RNG stream kinds */
-enum { ORC_RNG_XORWOW = 0, ORC_RNG_PHILOX = 1, ORC_RNG_MRG32K3A = 2 };
+enum { ORC_RNG_XORWOW = 0, ORC_RNG_PHILOX = 1, ORC_RNG_MRG32K3A = 2,
+       /* NOT a cuRAND stream: the product's opt-in dense-draw mapping (three (22-bit, 20-bit) draws per Philox block,
+        * nmch_b200/csrc/fe_kernels.cu), restated so that mode can be checked path by path; normal pairs only */
+       ORC_RNG_PHILOX_DENSE = 3 };
 /* variance floor g(.) : README.md:37-40 ; only abs is coded in the reference */
 enum { ORC_FLOOR_ABS = 0, ORC_FLOOR_PLUS = 1 };
 
@@ -47,6 +50,8 @@ typedef struct {
     int      pos;
     /* mrg32k3a (curand_kernel.h:208-215) */
     uint32_t s1[3], s2[3];
+    /* dense mapping: global step index */
+    uint64_t dense_step;
     /* Box-Muller caches (curand_normal.h:313-326, 581-596) */
     int      bm_flag;
     float    bm_extra;

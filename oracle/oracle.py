@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 CURAND_HOST_PATH = os.path.join(HERE, "_ref", "libcurand_host.so")
 REF_HARNESS_PATH = os.path.join(HERE, "_ref", "nmch_ref_harness")
 
-RNG_XORWOW, RNG_PHILOX, RNG_MRG32K3A = 0, 1, 2
+RNG_XORWOW, RNG_PHILOX, RNG_MRG32K3A, RNG_PHILOX_DENSE = 0, 1, 2, 3
 FLOOR_ABS, FLOOR_PLUS = 0, 1
 
 
@@ -30,7 +30,7 @@ class OrcRng(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("d", C.c_uint32), ("v", C.c_uint32 * 5),
         ("ctr", C.c_uint32 * 4), ("key", C.c_uint32 * 2), ("out", C.c_uint32 * 4), ("pos", C.c_int),
-        ("s1", C.c_uint32 * 3), ("s2", C.c_uint32 * 3),
+        ("s1", C.c_uint32 * 3), ("s2", C.c_uint32 * 3), ("dense_step", C.c_uint64),
         ("bm_flag", C.c_int), ("bm_extra", C.c_float), ("bm_flag_d", C.c_int), ("bm_extra_d", C.c_double),
     ]
 

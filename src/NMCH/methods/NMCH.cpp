@@ -65,7 +65,7 @@ void NMCH<rnd_state>::engine_init(int method, unsigned long long seed, float *ti
     case nmch::random::stream_mode::xorwow_compat: p.rng = NMCH_RNG_XORWOW_COMPAT; break;
     case nmch::random::stream_mode::philox_compat: p.rng = NMCH_RNG_PHILOX_COMPAT; break;
     case nmch::random::stream_mode::mrg32k3a_compat: p.rng = NMCH_RNG_MRG32K3A_COMPAT; break;
-    default: p.rng = philox_compat ? NMCH_RNG_PHILOX_COMPAT : NMCH_RNG_PHILOX; break;
+    default: p.rng = philox_compat ? NMCH_RNG_PHILOX_COMPAT : (philox_dense ? NMCH_RNG_PHILOX_DENSE : NMCH_RNG_PHILOX); break;
     }
     p.device = -1;
     p.paths_per_thread = paths_per_thread;

@@ -49,7 +49,7 @@ void usage(const char *argv0)
     printf("B200 engine options (actual defaults: NTPB 512, NB 512, N 1000):\n");
     printf("  --method qe        Quadratic-exponential large-step scheme (use with --N 50..100)\n");
     printf("  --g <abs|plus>     Variance floor g(.) (default: abs)\n");
-    printf("  --rng <philox|xorwow|philox-compat>  Stream mode (default: philox)\n");
+    printf("  --rng <philox|xorwow|philox-compat|philox-dense>  Stream mode (default: philox; philox-dense: fe only)\n");
     printf("  --gpus <int>       GPUs to shard the paths over (default: 1)\n");
     printf("  --paths-per-thread <int>  1, 2, 4 or 8 (default: auto)\n");
     printf("  --strikes <k1,k2,..>  Also price these strikes (and pathwise deltas) on a second pass of the streams\n");
@@ -63,6 +63,7 @@ int run(const Options &o)
     m.set_floor_plus(o.g == "plus");
     m.set_gpus(o.gpus);
     m.set_philox_compat(o.rng == "philox-compat");
+    m.set_philox_dense(o.rng == "philox-dense");
     m.set_paths_per_thread(o.ppt);
     m.init(o.seed);
     m.compute();
@@ -122,7 +123,7 @@ int main(int argc, char **argv)
         else if (strcmp(argv[i], "--json") == 0) o.json = true;
         else if (strcmp(argv[i], "--help") == 0) { usage(argv[0]); return 0; }
     }
-    if (o.rng != "philox" && o.rng != "xorwow" && o.rng != "philox-compat") {
+    if (o.rng != "philox" && o.rng != "xorwow" && o.rng != "philox-compat" && o.rng != "philox-dense") {
         printf("Unknown rng: %s\n", o.rng.c_str());
         return 1;
     }
