@@ -120,6 +120,33 @@ __device__ __forceinline__ float poisson_inversion(float mu, float u)
     return k;
 }
 
+// One trial of the chi-square split from three Philox words, every constant folded on the host, no data-dependent
+// branch:   2 V'/c = (Z + sqrt(2 l))^2 + 2 Gamma(a),   Z = c0 z', X = c0 x' from one Box-Muller pair.
+//   wa: top 23 bits -> radius uniform      wb: top 23 bits -> angle      wc: top 23 bits -> accept-test uniform
+//   the shape<1 boost uniform is spliced from the bits those mantissas leave over: wa[8:0] : wb[8:0] : wc[4:0]
+// Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp: accept iff v1 > 0 and
+//   log2 u < (x^2/2 + d (1 - v)) log2 e + d log2 v          (the exact test; no squeeze, hence no divergence)
+// Returns accept; zp = Z / c0, g2 = 2 Gamma(a).
+__device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t wc, const EmPoint &pc, float &zp, float &g2)
+{
+    const float rad = sqrt_approx(-lg2_approx(u01_open(wa)));
+    const float ang = bits_to_1_2(wb) * 6.2831855f;
+    zp = rad * sin_approx(ang);
+    const float xp = rad * cos_approx(ang);
+    const float v1 = fmaf(pc.f_c, xp, 1.0f);
+    const float v = v1 * v1 * v1;
+    const float x2 = xp * xp;
+    float rhs = fmaf(x2, pc.f_h, pc.f_dl * (1.0f - v));
+    rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
+    g2 = pc.f_g2 * v;
+    if (pc.inv_a != 0.0f) {                                      // shape < 1 boost: Gamma(a) = Gamma(a+1) U^(1/a)
+        const uint32_t m = ((wa & 0x1ffu) << 14) | ((wb & 0x1ffu) << 5) | (wc & 0x1fu);
+        const float ub = __uint_as_float(m | 0x3f800000u) - 0.99999994f;
+        g2 *= ex2_approx(pc.inv_a * lg2_approx(ub));
+    }
+    return (v1 > 0.0f) && (lg2_approx(u01_open(wc)) < rhs);
+}
+
 template <bool MIXED>
 __global__ void __launch_bounds__(256)
 em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__ pts, ReduceBuffers rb,
@@ -143,39 +170,42 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         };
         uint32_t blk = 0;
         int step = 0;
-        bool have_np = false;
-        float np = 0.0f;
-        // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive), so
-        // the loop terminates; the cap on the Poisson-mixture path is a belt against a hang: a path that exhausts it
-        // ends early and poisons the sum with NaN instead of stalling the GPU.  (The split path is not taxed with it.)
-        const uint32_t max_blocks = 64u * (uint32_t)L.N + 4096u;
-        while (step < L.N) {
-            if (MIXED && !pc.fast && blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
-            const U4 w = next_block(blk++);
-            float gsum;
-            bool accept;
-            if (!MIXED || pc.fast) {
-                // chi-square split, every constant folded on the host, no data-dependent branch:
-                //   2 V'/c = (Z + sqrt(2 l))^2 + 2 Gamma(a),   Z = c0 z', X = c0 x' from one Box-Muller pair
-                const float rad = sqrt_approx(-lg2_approx(u01_open(w.x)));
-                const float ang = bits_to_1_2(w.y) * 6.2831855f;
-                const float zp = rad * sin_approx(ang), xp = rad * cos_approx(ang);
-                // Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp: accept iff v1 > 0 and
-                //   log2 u < (x^2/2 + d (1 - v)) log2 e + d log2 v      (the exact test; no squeeze, no divergence)
-                const float v1 = fmaf(pc.f_c, xp, 1.0f);
-                const float v = v1 * v1 * v1;
-                const float x2 = xp * xp;
-                float rhs = fmaf(x2, pc.f_h, pc.f_dl * (1.0f - v));
-                rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
-                accept = (v1 > 0.0f) && (lg2_approx(u01_open(w.z)) < rhs);
-                float g2 = pc.f_g2 * v;
-                if (pc.inv_a != 0.0f) g2 *= ex2_approx(pc.inv_a * lg2_approx(u01_open(w.w)));   // shape < 1 boost
-                const float t = fmaf(1.17741002f, zp, sqrt_approx(pc.two_lc * V));
-                gsum = fmaf(t, t, g2);                          // = 2 V'/c
-            } else {
-                // Poisson mixture: first a Poisson draw (one trial per block), then, on a block of its own, one
-                // Marsaglia-Tsang trial for Gamma(d + N).  A lane that already holds N uses this iteration's block
-                // for the gamma trial directly, so a gamma retry never re-draws (and never biases) N.
+        if (!MIXED || pc.fast) {
+            // chi-square split.  A trial needs four 23-bit fields (radius, angle, accept-test uniform, shape<1 boost
+            // uniform) = 92 bits, so FOUR trials share THREE Philox blocks: trial j takes words 3j..3j+2 (em_fast_trial).
+            // The generator multiplies are the scarce resource, a quarter of them is saved.
+            // Only the last FFMA pair of a trial depends on V, so the four trials of a group overlap.
+            while (step < L.N) {
+                const U4 b0 = next_block(blk), b1 = next_block(blk + 1u), b2 = next_block(blk + 2u);
+                blk += 3u;
+                const uint32_t w[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float zp, g2;
+                    const bool ok = em_fast_trial(w[3 * j], w[3 * j + 1], w[3 * j + 2], pc, zp, g2);
+                    const float t = fmaf(1.17741002f, zp, sqrt_approx(pc.two_lc * V));
+                    const float gsum = fmaf(t, t, g2);          // = 2 V'/c
+                    if (ok && step < L.N) {
+                        const float Vn = __fmul_rn(pc.f_scale, gsum);
+                        vI = __fadd_rn(vI, __fadd_rn(V, Vn));   // trapezoid sum, NMCH_EM.cu:243
+                        V = Vn;
+                        ++step;
+                    }
+                }
+            }
+        } else {
+            // Poisson mixture (d <= 1/2): one trial per iteration on a fresh block.  First a Poisson draw, then, on a
+            // block of its own, one Marsaglia-Tsang trial for Gamma(d + N).  A lane that already holds N uses this
+            // iteration's block for the gamma trial directly, so a gamma retry never re-draws (and never biases) N.
+            // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive),
+            // so the loop terminates; the cap is a belt against a hang: a path that exhausts it ends early and poisons
+            // the sum with NaN instead of stalling the GPU.  (The split path is not taxed with it.)
+            bool have_np = false;
+            float np = 0.0f;
+            const uint32_t max_blocks = 64u * (uint32_t)L.N + 4096u;
+            while (step < L.N) {
+                if (blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
+                const U4 w = next_block(blk++);
                 U4 wg = w;
                 bool gamma_now = have_np;
                 if (!have_np) {
@@ -191,8 +221,6 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                         gamma_now = true;
                     }
                 }
-                accept = false;
-                gsum = 0.0f;
                 if (gamma_now) {
                     float x, unused;
                     box_muller_fast(wg.x, wg.y, x, unused);
@@ -204,16 +232,14 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                     const float md = shape - (1.0f / 3.0f);
                     const float mc = rsqrt_approx(9.0f * md);
                     float gam;
-                    accept = mt_trial(x, u01_open(wg.z), md, mc, gam);
-                    gsum = 2.0f * gam * boost;                  // same convention as the split: gsum = 2 V'/c
+                    if (mt_trial(x, u01_open(wg.z), md, mc, gam)) {
+                        const float Vn = __fmul_rn(pc.f_scale, 2.0f * gam * boost);   // f_scale = c / 2
+                        vI = __fadd_rn(vI, __fadd_rn(V, Vn));
+                        V = Vn;
+                        ++step;
+                        have_np = false;
+                    }
                 }
-            }
-            if (accept) {
-                const float Vn = __fmul_rn(pc.f_scale, gsum);  // explicit roundings: both instantiations agree bit for bit
-                vI = __fadd_rn(vI, __fadd_rn(V, Vn));          // trapezoid sum, NMCH_EM.cu:243
-                V = Vn;
-                ++step;
-                have_np = false;
             }
         }
         // terminal draw (NMCH_EM.cu:247-260, generalised to S_0, r, T)

@@ -61,5 +61,20 @@ int main()
     run<0, 9, 12, 4>("... without the IMAD.WIDE", d, sms, ghz);
     run<8, 0, 0, 0>("8 IMAD.WIDE only", d, sms, ghz);
     run<7, 9, 12, 4>("dense-like: 6.6 -> 7 IMAD.WIDE", d, sms, ghz);
+    // which second limit blends in below ~45 cycles (dense FE mode, EM trial)?  Single pipes and pairs:
+    run<0, 9, 12, 0>("9 LOP3 + 2 SHF + 12 FP32", d, sms, ghz);
+    run<0, 9, 0, 4>("9 LOP3 + 2 SHF + 4 MUFU", d, sms, ghz);
+    run<0, 0, 12, 4>("2 SHF + 12 FP32 + 4 MUFU", d, sms, ghz);
+    run<0, 0, 0, 4>("2 SHF + 4 MUFU", d, sms, ghz);
+    run<0, 9, 0, 0>("9 LOP3 + 2 SHF", d, sms, ghz);
+    run<0, 0, 12, 0>("2 SHF + 12 FP32", d, sms, ghz);
+    run<6, 10, 11, 4>("dense FE (3 steps/block): 5.5 -> 6 IMAD.WIDE, 10 LOP3, 11 FP32, 4 MUFU", d, sms, ghz);
+    run<5, 10, 11, 4>("... with 5 IMAD.WIDE", d, sms, ghz);
+    run<4, 10, 11, 4>("... with 4 IMAD.WIDE", d, sms, ghz);
+    run<6, 10, 11, 3>("... 6 IMAD.WIDE, 3 MUFU", d, sms, ghz);
+    run<6, 10, 11, 2>("... 6 IMAD.WIDE, 2 MUFU", d, sms, ghz);
+    run<14, 18, 24, 9>("EM trial (4 per 3 blocks): 13.5 -> 14 IMAD.WIDE, 18 LOP3, 24 FP32, 9 MUFU", d, sms, ghz);
+    run<12, 18, 24, 9>("... with 12 IMAD.WIDE", d, sms, ghz);
+    run<18, 18, 24, 9>("... with 18 IMAD.WIDE (one block per trial)", d, sms, ghz);
     return 0;
 }
