@@ -366,7 +366,7 @@ def main():
                     dms = min(de.compute().exec_ms for _ in range(3))
                 dval = units_per_gpu_step / (dms * 1e-3)
                 line["dense_mode"] = {"value": dval, "unit": unit, "ms_per_step": dms, "roofline_frac": dval / peak,
-                                      "note": "NMCH_RNG_PHILOX_DENSE: three (22-bit, 20-bit) draws per Philox block; "
+                                      "note": "NMCH_RNG_PHILOX_DENSE: three (23-bit, 19-bit) draws per Philox block; "
                                               "statistically equivalent, not cuRAND-word-compatible; bench.py --rng dense"}
             except Exception as ex:  # noqa: BLE001
                 line["dense_mode"] = {"error": str(ex)[:200]}

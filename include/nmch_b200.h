@@ -42,7 +42,7 @@ typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
  *                  contraction as the reference's CUDA build
  *   PHILOX_COMPAT  curandStatePhilox4_32_10_t-compatible (reference CLI default, nmch.cu:119,130)
  *   MRG32K3A_COMPAT curandStateMRG32k3a_t-compatible (the third tag the reference instantiates, NMCH.cu:31)
- *   PHILOX_DENSE   opt-in FE throughput mode: the same Philox4x32-10 blocks cut into THREE (22-bit radius, 20-bit
+ *   PHILOX_DENSE   opt-in FE throughput mode: the same Philox4x32-10 blocks cut into THREE (23-bit radius, 19-bit
  *                  angle) draws instead of two word pairs, i.e. a third fewer generator multiplies per step.  Statistically
  *                  equivalent, NOT word-compatible with cuRAND's per-step layout (checked against a restatement of its
  *                  own mapping and against the semi-analytic price) */

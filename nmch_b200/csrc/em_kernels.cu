@@ -147,8 +147,17 @@ __device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t
     return (v1 > 0.0f) && (lg2_approx(u01_open(wc)) < rhs);
 }
 
+// Block shape of the native kernel (tuning builds may override: -DNMCHB_EM_THREADS=.. -DNMCHB_EM_MINB=..)
+#ifndef NMCHB_EM_THREADS
+#define NMCHB_EM_THREADS 256
+#endif
+#ifndef NMCHB_EM_MINB
+#define NMCHB_EM_MINB 6
+#endif
+constexpr int kEmThreads = NMCHB_EM_THREADS;
+
 template <bool MIXED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kEmThreads, NMCHB_EM_MINB)
 em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__ pts, ReduceBuffers rb,
                  float *__restrict__ S_out, float *__restrict__ V_out)
 {
@@ -525,7 +534,7 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
 {
     const nmch_params_t &p = e->p;
     const bool own = (k == nullptr);
-    const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
+    unsigned long long bpp = (e->n_local + (unsigned long long)kEmThreads - 1ull) / (unsigned long long)kEmThreads;
     if (bpp == 0 || bpp > 0x7fffffffull) return engine_fail(NMCH_ERR_ARG, "launch grid out of range");
     cudaError_t err;
     if (p.rng == NMCH_RNG_PHILOX) {
@@ -565,20 +574,21 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
         dim3 grid((unsigned)bpp, (unsigned)n_points, 1);
         cudaFuncAttributes attr{};
         if (all_fast) {
-            em_native_kernel<false><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            em_native_kernel<false><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
             cudaFuncGetAttributes(&attr, em_native_kernel<false>);
         } else {
-            em_native_kernel<true><<<grid, 256, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            em_native_kernel<true><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
             cudaFuncGetAttributes(&attr, em_native_kernel<true>);
         }
         err = cudaGetLastError();
         if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_native_kernel", err);
-        e->kinfo = KernelInfo{(int)grid.x, (int)grid.y, 256, 1, attr.numRegs,
+        e->kinfo = KernelInfo{(int)grid.x, (int)grid.y, kEmThreads, 1, attr.numRegs,
                               (int)(sizeof(EmLaunch) + sizeof(const EmPoint *) + sizeof(ReduceBuffers) + 2 * sizeof(float *))};
         e->em_calls += (unsigned long long)n_points;
         return NMCH_OK;
     }
     // compat modes
+    bpp = (e->n_local + 255ull) / 256ull;
     int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(RawPoint));
     if (rc) return rc;
     const RawPoint *d_pts = nullptr;

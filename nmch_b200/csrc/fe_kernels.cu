@@ -165,25 +165,27 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
 // ------------------------------------------------------------------------------------------
 // dense-draw variant (opt-in stream mode NMCH_RNG_PHILOX_DENSE): THREE steps per Philox block.
 // The product kernel is bound by the 32x32->64 multiplies of Philox; this variant spends a third
-// fewer of them by cutting each 128-bit block into three (22-bit radius, 20-bit angle) field pairs instead of two
-// (32, 32) word pairs.  The price: a (path, step) no longer consumes the words cuRAND's layout assigns to it, so this
-// mode is checked against a restatement of ITS mapping and statistically, not against the reference's Philox stream.
-//   step A: radius = x[31:10]              angle = x[9:0]  : y[31:22]
-//   step B: radius = y[21:0]               angle = z[31:12]
-//   step C: radius = z[11:0] : w[31:22]    angle = w[21:2]                 (2 bits unused)
+// fewer of them by cutting each 128-bit block into three (23-bit radius, 19-bit angle) field pairs instead of two
+// (32, 32) word pairs.  The radius uniform keeps the 23 bits of the native mode (same tails); only the angle is
+// coarser, and an equispaced angle grid of 2^19 points leaves every trigonometric moment below that order exact.
+// The price: a (path, step) no longer consumes the words cuRAND's layout assigns to it, so this mode is checked
+// against a restatement of ITS mapping and statistically, not against the reference's Philox stream.
+//   step A: radius = x[31:9]               angle = x[8:0]  : y[31:22]
+//   step B: radius = y[21:0] : z[31]       angle = z[30:12]
+//   step C: radius = z[11:0] : w[31:21]    angle = w[20:2]                 (2 bits unused)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dense_fields(const U4 &w, int phase, float &f1, float &f2)
 {
-    uint32_t r, a;                                   // mantissas: radius field << 1, angle field << 3
+    uint32_t r, a;                                   // mantissas: 23-bit radius field, angle field << 4
     if (phase == 0) {
-        r = (w.x >> 9) & 0x7ffffeu;
-        a = __funnelshift_r(w.y, w.x, 19) & 0x7ffff8u;
+        r = w.x >> 9;
+        a = __funnelshift_r(w.y, w.x, 18) & 0x7ffff0u;
     } else if (phase == 1) {
-        r = (w.y << 1) & 0x7ffffeu;
-        a = (w.z >> 9) & 0x7ffff8u;
+        r = __funnelshift_r(w.z, w.y, 31) & 0x7fffffu;
+        a = (w.z >> 8) & 0x7ffff0u;
     } else {
-        r = __funnelshift_r(w.w, w.z, 21) & 0x7ffffeu;
-        a = (w.w << 1) & 0x7ffff8u;
+        r = __funnelshift_r(w.w, w.z, 21) & 0x7fffffu;
+        a = (w.w << 2) & 0x7ffff0u;
     }
     f1 = __uint_as_float(r | 0x3f800000u);
     f2 = __uint_as_float(a | 0x3f800000u);
@@ -195,7 +197,7 @@ __device__ __forceinline__ void fe_step_dense(float &S, float &V, const U4 &w, i
 {
     float f1, f2;
     dense_fields(w, phase, f1, f2);
-    const float u = f1 - 0.99999988f;                 // (k22 + 0.5) * 2^-22, in (0,1): exact
+    const float u = f1 - 0.99999994f;                 // (k23 + 0.5) * 2^-23, in (0,1): exact, as the native mode
     const float l2 = lg2_approx(u);
     const float q = sqrt_approx(-(V * l2));
     const float ang = f2 * 6.2831855f;

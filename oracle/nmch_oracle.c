@@ -321,12 +321,12 @@ void orc_normal2(orc_rng_t *s, float *gx, float *gy)
         const uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), s->ctr[2], s->ctr[3]};
         uint32_t w[4];
         orc_philox4x32_10(ctr, s->key, w);
-        uint32_t k22, k20;
-        if (phase == 0) { k22 = w[0] >> 10; k20 = ((w[0] & 0x3ffu) << 10) | (w[1] >> 22); }
-        else if (phase == 1) { k22 = w[1] & 0x3fffffu; k20 = w[2] >> 12; }
-        else { k22 = ((w[2] & 0xfffu) << 10) | (w[3] >> 22); k20 = (w[3] >> 2) & 0xfffffu; }
-        const float u = ((float)k22 + 0.5f) * 2.3841858e-07f;            /* 2^-22 */
-        const float ang = (1.0f + (float)k20 * 9.5367432e-07f) * 6.2831855f;  /* 2^-20 */
+        uint32_t k23, k19;
+        if (phase == 0) { k23 = w[0] >> 9; k19 = ((w[0] & 0x1ffu) << 10) | (w[1] >> 22); }
+        else if (phase == 1) { k23 = ((w[1] & 0x3fffffu) << 1) | (w[2] >> 31); k19 = (w[2] >> 12) & 0x7ffffu; }
+        else { k23 = ((w[2] & 0xfffu) << 11) | (w[3] >> 21); k19 = (w[3] >> 2) & 0x7ffffu; }
+        const float u = ((float)k23 + 0.5f) * 1.1920929e-07f;            /* 2^-23 */
+        const float ang = (1.0f + (float)k19 * 1.9073486e-06f) * 6.2831855f;  /* 2^-19 */
         const float r = sqrtf(-2.0f * logf(u));
         *gx = sinf(ang) * r;
         *gy = cosf(ang) * r;

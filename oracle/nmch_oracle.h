@@ -27,7 +27,7 @@ extern "C" {
 
 /* RNG stream kinds */
 enum { ORC_RNG_XORWOW = 0, ORC_RNG_PHILOX = 1, ORC_RNG_MRG32K3A = 2,
-       /* NOT a cuRAND stream: the product's opt-in dense-draw mapping (three (22-bit, 20-bit) draws per Philox block,
+       /* NOT a cuRAND stream: the product's opt-in dense-draw mapping (three (23-bit, 19-bit) draws per Philox block,
         * nmch_b200/csrc/fe_kernels.cu), restated so that mode can be checked path by path; normal pairs only */
        ORC_RNG_PHILOX_DENSE = 3 };
 /* variance floor g(.) : README.md:37-40 ; only abs is coded in the reference */

@@ -1,4 +1,4 @@
-"""Opt-in dense-draw FE stream mode (NMCH_RNG_PHILOX_DENSE: three (22-bit radius, 20-bit angle) draws per Philox
+"""Opt-in dense-draw FE stream mode (NMCH_RNG_PHILOX_DENSE: three (23-bit radius, 19-bit angle) draws per Philox
 block), through the C ABI.  It is NOT word-compatible with cuRAND's per-step layout, so the checkers are: a
 restatement of its own mapping in the oracle (per path), exact moment identities of the Euler scheme (they isolate
 the quality of the normals), and the semi-analytic price."""

@@ -5,6 +5,7 @@ Sources of truth: Random123 Philox KATs, the SURVEY.md §8c vectors, and tests/g
 Integer streams: bit exact.  Floats: same host libm on both sides, tolerance 2e-7 relative.
 """
 import json
+import math
 import os
 
 import numpy as np
@@ -118,3 +119,33 @@ def test_poisson_mean_bias_documented():
     m = sum(r.poisson(lam) for _ in range(n)) / n
     se = np.sqrt(lam / n)
     assert abs(m - lam) < 6 * se + 0.5     # sane, but not required to be unbiased
+
+
+def test_dense_mapping_restatement_is_self_consistent():
+    """The opt-in dense FE stream (three (23-bit radius, 19-bit angle) draws per Philox block) has no cuRAND
+    counterpart; pin the oracle's restatement of it against an independent bit-level statement of the field layout
+    (nmch_b200/csrc/fe_kernels.cu: dense_fields) and against the moments of a standard normal pair."""
+    seed, path = 77, 5
+    r = o.Rng(o.RNG_PHILOX_DENSE, seed, path, 0)
+    got = [r.normal2() for _ in range(9)]
+    for step, (gx, gy) in enumerate(got):
+        blk, phase = divmod(step, 3)
+        x, y, z, w = o.philox4x32_10([blk & 0xffffffff, blk >> 32, path, 0], [seed, 0])
+        bits = (x << 96) | (y << 64) | (z << 32) | w                  # 128-bit block, x first
+        lo = 128 - 42 * (phase + 1)                                    # three 42-bit fields from the top
+        field = (bits >> lo) & ((1 << 42) - 1)
+        k23, k19 = field >> 19, field & ((1 << 19) - 1)
+        u = (k23 + 0.5) * 2.0 ** -23
+        ang = 2.0 * math.pi * k19 * 2.0 ** -19
+        rad = math.sqrt(-2.0 * math.log(u))
+        assert gx == pytest.approx(rad * math.sin(ang), rel=2e-5, abs=2e-6)
+        assert gy == pytest.approx(rad * math.cos(ang), rel=2e-5, abs=2e-6)
+    n = 60000
+    r = o.Rng(o.RNG_PHILOX_DENSE, 1, 0, 0)
+    g = np.array([r.normal2() for _ in range(n)], dtype=np.float64)
+    flat = g.ravel()
+    assert abs(flat.mean()) < 4 / math.sqrt(2 * n)
+    assert abs(flat.var() - 1.0) < 4 * math.sqrt(2.0 / (2 * n))
+    assert abs((flat ** 4).mean() - 3.0) < 4 * math.sqrt(96.0 / (2 * n))
+    assert abs((g[:, 0] * g[:, 1]).mean()) < 4 / math.sqrt(n)
+    assert abs((g[:-1, 0] * g[1:, 0]).mean()) < 4 / math.sqrt(n)        # consecutive steps (within and across blocks)
