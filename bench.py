@@ -37,6 +37,12 @@ ISSUE_PER_CLK_PER_SM = min(128.0 / 42.0, 16.0 / 5.0)      # 42 t
 # profiles/r01_fe_mix_bound.txt: the FE kernel's own instruction mix, issued from independent chains on this GPU,
 # needs 55.04 cycles per warp-step per SM sub-partition (the Philox IMAD.WIDE.U32 costs ~5.2 issue cycles)
 MIX_BOUND_CYCLES_PER_WARP_STEP = 55.04
+# SURVEY.md §8d for EM: "estimate 90-100 instr/step => 3.9e8 paths/s/GPU ceiling at N=1000" = 95 thread-instr per
+# path-step at one instruction per scheduler per clock
+EM_INSTR_PER_PATH_STEP = 95.0
+# profiles/r01_fe_mix_bound_dense_em.txt: the EM trial's instruction mix (14 IMAD.WIDE, 18 LOP3, 2 SHF, 24 FP32,
+# 9 MUFU) from independent chains needs 96.83 cycles per warp-trial per SM sub-partition; 1.045 trials per step
+EM_MIX_BOUND_CYCLES_PER_WARP_STEP = 96.83 * 1.045
 
 
 # ------------------------------------------------------------------------------------------------
@@ -322,10 +328,10 @@ def main():
         if args.method == "fe":
             peak = info["sm_count"] * f_hz * ISSUE_PER_CLK_PER_SM
         else:
-            # EM has no budget in SURVEY §8d.  Cost model measured for the FE kernel: an IMAD.WIDE.U32
-            # costs ~5.2 FMA-pipe cycles, an FP32 op ~1; one EM trial has 18 + 24 of them and a step takes 1.045 trials
-            cycles_per_warp_step = (18 * 5.2 + 24) * 1.045
-            peak = info["sm_count"] * f_hz * 4 * 32 / (cycles_per_warp_step * N)
+            peak = info["sm_count"] * f_hz * 128.0 / (EM_INSTR_PER_PATH_STEP * N)
+        # measured bound of the kernel's own instruction mix on this GPU (profiles/microbench/fe_mix_bound.cu)
+        mix_peak = (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP if args.method == "fe" else
+                    info["sm_count"] * f_hz * 4 * 32 / (EM_MIX_BOUND_CYCLES_PER_WARP_STEP * N))
         traffic = None
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj):
@@ -345,14 +351,11 @@ def main():
                          "traffic": traffic,
                          "model": "SURVEY.md §8d: SMs x f x min(128/42 issue, 16/5 MUFU) path-steps/s; f = median SM clock "
                                   "sampled during the timed region; per-GPU achieved" if args.method == "fe" else
-                                  "no SURVEY budget for EM: FMA-pipe cost model of DESIGN.md §4.1/4.3 -- (18 IMAD.WIDE x 5.2 + 24 FP32) "
-                                  "cycles per warp-trial x 1.045 trials per step x N steps; paths/s per GPU",
+                                  "SURVEY.md §8d estimate for EM: SMs x f x 128 / (95 thread-instr per path-step x N) paths/s "
+                                  "(data-dependent scheme: reported, not targeted); f as for FE; per-GPU achieved",
                          "peak_at_max_clock": (info["sm_count"] * (ck["sm_max_mhz"] or 1965) * 1e6 * ISSUE_PER_CLK_PER_SM
                                                if args.method == "fe" else None),
-                         "mix_bound_peak": (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP
-                                            if args.method == "fe" else None),
-                         "mix_bound_frac": (per_gpu / (info["sm_count"] * f_hz * 4 * 32 / MIX_BOUND_CYCLES_PER_WARP_STEP)
-                                            if args.method == "fe" else None)},
+                         "mix_bound_peak": mix_peak, "mix_bound_frac": per_gpu / mix_peak},
             "kernel": {k: info[k] for k in ("grid_x", "grid_y", "block_threads", "paths_per_thread", "regs_per_thread", "sm_count")},
             "result": {"E[X]": mean, "var": var, "std_error": (var / n_total) ** 0.5,
                        "heston_semi_analytic": 0.1197325094 if args.method in ("fe", "em") else None},

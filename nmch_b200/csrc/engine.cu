@@ -107,6 +107,10 @@ void fill_fe_launch(const nmch_engine *e, FeLaunch &L, int n_points, int blocks_
     L.first_path = e->first_path;
     L.n_local = e->n_local;
     L.draw_offset = e->draw_offset;
+    L.dense_q0 = (e->draw_offset >> 1) / 3ull;
+    L.dense_r0 = (unsigned int)((e->draw_offset >> 1) % 3ull);
+    L.dense_qN = (unsigned int)p.N / 3u;
+    L.dense_rN = (unsigned int)p.N % 3u;
     L.N = p.N;
     L.n_points = n_points;
     L.blocks_per_point = blocks_per_point;

@@ -219,9 +219,13 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
     constexpr int TILE = P * THREADS;
     const int point = blockIdx.y;
     const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
-    // stream position in STEPS: draw_offset counts two logical draws per step, like the other modes
-    const unsigned long long s0 = (L.draw_offset >> 1) + (unsigned long long)point * (unsigned long long)L.N;
-    const int phase0 = (int)(s0 % 3ull);
+    // stream position in STEPS (draw_offset counts two logical draws per step, like the other modes):
+    //   s0 = draw_offset / 2 + point * N = 3 * blk0 + phase0, from the host's pre-divided parts -- a 64-bit division
+    //   here would take the block index, and with it the path-independent Philox multiplies, off the uniform datapath
+    const unsigned int t0 = L.dense_r0 + (unsigned int)point * L.dense_rN;
+    const unsigned int q0 = (t0 * 43691u) >> 17;      // t0 / 3, exact below 2^17 (t0 <= 2 + 2 * 65534): low multiply + shift only
+    const unsigned long long blk0 = L.dense_q0 + (unsigned long long)point * (unsigned long long)L.dense_qN + (unsigned long long)q0;
+    const int phase0 = (int)(t0 - 3u * q0);
 
     __shared__ double2 s_acc[THREADS];
     s_acc[threadIdx.x] = make_double2(0.0, 0.0);
@@ -230,7 +234,10 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
         const unsigned long long local0 = tile * TILE;
         if (local0 >= L.n_local) break;
         const unsigned long long g0 = L.first_path + local0;
-        const uint32_t path_hi = (uint32_t)(g0 >> 32);
+        uint32_t path_hi = (uint32_t)(g0 >> 32);
+#ifndef NMCHB_DENSE_NO_PIN
+        asm volatile("" : "+r"(path_hi));                         // one register, instead of re-deriving it from the tile index every iteration
+#endif
         const uint32_t path_lo0 = (uint32_t)g0 + threadIdx.x;
         float S[P], V[P];
 #pragma unroll
@@ -238,14 +245,16 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
             S[j] = L.S0;
             V[j] = L.v0;
         }
-        unsigned long long blk = s0 / 3ull;
+        unsigned long long blk = blk0;
         int n = L.N;
         if (phase0 != 0 && n > 0) {                               // finish the block a previous call left half used
             const int cnt = min(3 - phase0, n);
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
-                for (int ph = phase0; ph < phase0 + cnt; ++ph) fe_step_dense<FLOOR>(S[j], V[j], w, ph, L, pc);
+#pragma unroll
+                for (int ph = 1; ph < 3; ++ph)                    // static phases: the field extraction stays branch-free
+                    if (ph >= phase0 && ph < phase0 + cnt) fe_step_dense<FLOOR>(S[j], V[j], w, ph, L, pc);
             }
             ++blk;
             n -= cnt;
@@ -278,7 +287,9 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
-                for (int ph = 0; ph < rest; ++ph) fe_step_dense<FLOOR>(S[j], V[j], w, ph, L, pc);
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph)
+                    if (ph < rest) fe_step_dense<FLOOR>(S[j], V[j], w, ph, L, pc);
             }
         }
         double2 acc = s_acc[threadIdx.x];

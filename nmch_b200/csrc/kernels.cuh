@@ -27,6 +27,10 @@ struct FeLaunch {
     unsigned long long first_path;      // global index of local path 0 (= Philox subsequence of path 0)
     unsigned long long n_local;         // paths simulated by this engine
     unsigned long long draw_offset;     // u32 words each path has already consumed (stream position of point 0)
+    // dense mode: the same position in STEPS, pre-divided on the host so that the kernel needs no 64-bit division
+    // (which would leave the uniform datapath):  draw_offset / 2 = 3 * dense_q0 + dense_r0,  N = 3 * dense_qN + dense_rN
+    unsigned long long dense_q0;
+    unsigned int dense_r0, dense_qN, dense_rN;
     int   N;                            // time steps
     int   n_points;
     int   blocks_per_point;

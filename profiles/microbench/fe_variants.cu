@@ -102,6 +102,65 @@ __global__ void __launch_bounds__(THREADS, MINB) fe(const __grid_constant__ Cons
             }
             ++blk;
         }
+    } else if (VARIANT == 4 || VARIANT == 5 || VARIANT == 6 || VARIANT == 7) {
+        // 4: hand-hoisted product loop (what fe_philox_kernel runs).  5: the same with the two multiplies that do not
+        // depend on the path (M0 * block_lo and M1 * (hi ^ path_hi ^ k1[0])) read from a per-block shared-memory table
+        // instead of being recomputed by every thread.  6 / 7: the same pair for the 3-steps-per-block dense loop.
+        constexpr bool TABLE = (VARIANT == 5 || VARIANT == 7);
+        constexpr bool DENSE = (VARIANT >= 6);
+        const int iters = DENSE ? c.N / 3 : c.N / 2;
+        __shared__ uint4 tab[TABLE ? 512 : 1];
+        if (TABLE) {
+            for (int i = threadIdx.x; i < iters; i += THREADS) {
+                const unsigned long long sv = (unsigned long long)kPhiloxM0 * (uint32_t)i;
+                const uint32_t c2 = (uint32_t)(sv >> 32) ^ 0u ^ c.keys.k1[0];
+                const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2;
+                tab[i] = make_uint4((uint32_t)(p1 >> 32) ^ c.keys.k0[1], (uint32_t)p1, (uint32_t)sv ^ c.keys.k1[1], 0u);
+            }
+            __syncthreads();
+        }
+        PhiloxPathInv inv[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) inv[j] = philox_path_invariants(0u, path0 + j * THREADS, c.keys);
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            uint32_t e0, e1, e2;
+            if (TABLE) {
+                const uint4 t = tab[it];
+                e0 = t.x; e1 = t.y; e2 = t.z;
+            } else {
+                const unsigned long long sv = (unsigned long long)kPhiloxM0 * (uint32_t)it;
+                const uint32_t c2 = (uint32_t)(sv >> 32) ^ 0u ^ c.keys.k1[0];
+                const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2;
+                e0 = (uint32_t)(p1 >> 32) ^ c.keys.k0[1]; e1 = (uint32_t)p1; e2 = (uint32_t)sv ^ c.keys.k1[1];
+            }
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                uint32_t c0 = e0 ^ inv[j].lo1, c1 = e1, c2 = inv[j].q_hi ^ e2, c3 = inv[j].q_lo;
+#pragma unroll
+                for (int r = 2; r < 10; ++r) {
+                    const unsigned long long a = (unsigned long long)kPhiloxM0 * c0;
+                    const unsigned long long b = (unsigned long long)kPhiloxM1 * c2;
+                    const uint32_t n0 = (uint32_t)(b >> 32) ^ c1 ^ c.keys.k0[r];
+                    const uint32_t n2 = (uint32_t)(a >> 32) ^ c3 ^ c.keys.k1[r];
+                    c1 = (uint32_t)b; c3 = (uint32_t)a; c0 = n0; c2 = n2;
+                }
+                if (DENSE) {
+                    const uint32_t rA = (c0 >> 9) | 0x3f800000u;
+                    const uint32_t aA = (__funnelshift_r(c1, c0, 18) & 0x7ffff0u) | 0x3f800000u;
+                    const uint32_t rB = (__funnelshift_r(c2, c1, 31) & 0x7fffffu) | 0x3f800000u;
+                    const uint32_t aB = ((c2 >> 8) & 0x7ffff0u) | 0x3f800000u;
+                    const uint32_t rC = (__funnelshift_r(c3, c2, 21) & 0x7fffffu) | 0x3f800000u;
+                    const uint32_t aC = ((c3 << 2) & 0x7ffff0u) | 0x3f800000u;
+                    step_f<MODE>(S[j], V[j], __uint_as_float(rA), __uint_as_float(aA), c);
+                    step_f<MODE>(S[j], V[j], __uint_as_float(rB), __uint_as_float(aB), c);
+                    step_f<MODE>(S[j], V[j], __uint_as_float(rC), __uint_as_float(aC), c);
+                } else {
+                    step<MODE>(S[j], V[j], c0, c1, c);
+                    step<MODE>(S[j], V[j], c2, c3, c);
+                }
+            }
+        }
     } else {
 #pragma unroll 1
         for (int it = 0; it < c.N / 5; ++it) {
@@ -166,12 +225,14 @@ int main()
     double *d_out;
     cudaMalloc(&d_out, 8);
     c.N = 999;
-    run<4, 128, 10, 0, 0>("product loop (N=998)", c, d_out);
-    run<4, 128, 10, 3, 0>("3 steps per block (22/20-bit fields), minb 10", c, d_out);
-    run<4, 128, 8, 3, 0>("3 steps per block, minb 8", c, d_out);
-    run<4, 256, 5, 3, 0>("3 steps per block, 256 thr minb 5", c, d_out);
-    run<2, 128, 12, 3, 0>("3 steps per block, P=2 minb 12", c, d_out);
-    run<8, 128, 6, 3, 0>("3 steps per block, P=8 minb 6", c, d_out);
-    run<4, 128, 10, 3, 1>("3 steps per block, (.)+ floor", c, d_out);
+    run<4, 128, 10, 0, 0>("product loop (N=998), compiler-hoisted", c, d_out);
+    run<4, 128, 10, 4, 0>("product loop, hand-hoisted", c, d_out);
+    run<4, 128, 10, 5, 0>("product loop, shared multiplies from smem table", c, d_out);
+    run<8, 128, 6, 5, 0>("... table, P=8 minb 6", c, d_out);
+    run<2, 128, 12, 5, 0>("... table, P=2 minb 12", c, d_out);
+    run<4, 128, 10, 6, 0>("3 steps per block (23/19-bit fields), hand-hoisted", c, d_out);
+    run<4, 128, 10, 7, 0>("3 steps per block, smem table", c, d_out);
+    run<2, 128, 12, 7, 0>("3 steps per block, smem table, P=2 minb 12", c, d_out);
+    run<2, 128, 12, 6, 0>("3 steps per block, hand-hoisted, P=2 minb 12", c, d_out);
     return 0;
 }
