@@ -165,12 +165,16 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
     const EmPoint pc = (pts != nullptr) ? pts[point] : L.pt0;
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
-    const unsigned long long g = L.first_path + idx;
-    const uint32_t path_lo = (uint32_t)g, path_hi = (uint32_t)(g >> 32);
+    // first_path is a multiple of 4096 (checked at create): the high counter word is the same for the whole
+    // block, so the multiplies of a Philox block that do not depend on the path stay on the uniform datapath
+    const unsigned long long g0 = L.first_path + (unsigned long long)blockIdx.x * blockDim.x;
+    const uint32_t path_lo = (uint32_t)g0 + threadIdx.x;
+    uint32_t path_hi = (uint32_t)(g0 >> 32);
+    asm volatile("" : "+r"(path_hi));                       // computed once, not re-derived from blockIdx in the loop
     const uint32_t stream = L.call0 + (uint32_t)point;      // ctr.y: one stream per compute() call / point
 
     float V = L.v0, vI = 0.0f, S = 0.0f;
-    if (valid) {
+    {
         // counter = (trial block, stream, path_lo, path_hi): everything but the first word is fixed for this path
         const PhiloxPathInv inv = philox_path_invariants(stream, path_lo, L.keys);
         auto next_block = [&](uint32_t b) {
@@ -178,13 +182,14 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
             return philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv, L.keys);
         };
         uint32_t blk = 0;
-        int step = 0;
+        int step = valid ? 0 : L.N;                          // lanes past the end of the shard take part in the votes only
         if (!MIXED || pc.fast) {
             // chi-square split.  A trial needs four 23-bit fields (radius, angle, accept-test uniform, shape<1 boost
             // uniform) = 92 bits, so FOUR trials share THREE Philox blocks: trial j takes words 3j..3j+2 (em_fast_trial).
             // The generator multiplies are the scarce resource, a quarter of them is saved.
             // Only the last FFMA pair of a trial depends on V, so the four trials of a group overlap.
-            while (step < L.N) {
+            // The loop is warp-uniform (vote): the block counter is the same in every lane.
+            while (__any_sync(0xffffffffu, step < L.N)) {
                 const U4 b0 = next_block(blk), b1 = next_block(blk + 1u), b2 = next_block(blk + 2u);
                 blk += 3u;
                 const uint32_t w[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};

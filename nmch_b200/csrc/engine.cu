@@ -320,7 +320,7 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if ((p.rng == NMCH_RNG_PHILOX || p.rng == NMCH_RNG_PHILOX_DENSE ||
          (p.rng == NMCH_RNG_PHILOX_COMPAT && p.method == NMCH_METHOD_FE)) &&
         !is_multiple_of(p.first_path, kMaxTilePaths))
-        return fail(NMCH_ERR_ARG, "the Philox FE modes need first_path to be a multiple of 4096");
+        return fail(NMCH_ERR_ARG, "the native Philox modes (and Philox-compatible FE) need first_path to be a multiple of 4096");
     if (p.paths_per_thread != 0 && p.paths_per_thread != 1 && p.paths_per_thread != 2 && p.paths_per_thread != 4 &&
         p.paths_per_thread != 8)
         return fail(NMCH_ERR_ARG, "paths_per_thread must be 0 (auto), 1, 2, 4 or 8");

@@ -54,6 +54,12 @@ def test_argument_validation_needs_no_gpu(lib):
     p.first_path = 100                                                               # not a multiple of 4096
     assert lib.nmch_engine_create(C.byref(p), C.byref(h)) == capi.ERR_ARG
     assert b"4096" in lib.nmch_last_error()
+    p.method = 1                                                                     # native EM: same alignment rule
+    assert lib.nmch_engine_create(C.byref(p), C.byref(h)) == capi.ERR_ARG            # (block-uniform high counter word)
+    assert b"4096" in lib.nmch_last_error()
+    p.method, p.first_path, p.rng = 1, 0, 4                                          # the dense stream is an FE mode
+    assert lib.nmch_engine_create(C.byref(p), C.byref(h)) == capi.ERR_ARG
+    assert b"FE stream mode" in lib.nmch_last_error()
 
 
 def test_no_cpu_fallback(lib):
