@@ -28,7 +28,6 @@ namespace nmchb {
 // ------------------------------------------------------------------------------------------
 struct EmPoint {
     float scale;        // c
-    float two_lc;       // 2 * lc
     float lc;
     float d;            // 2 k theta / sigma^2
     float a;            // fast path: gamma shape d - 1/2 (boosted by +1 when < 1)
@@ -38,8 +37,10 @@ struct EmPoint {
     float f_c;          // mt_c * c0
     float f_h;          // 0.5 * c0^2 * log2(e)    log test, log2 domain
     float f_dl;         // mt_d * log2(e)
-    float f_g2;         // 2 * mt_d                gamma term of 2 * (V'/c)
-    float f_scale;      // c / 2
+    float f_g2s;        // mt_d * c                gamma term of V' = (c/2) (t^2 + 2 Gamma(a))
+    float f_t1;         // c0 * sqrt(c/2)          V' = (f_t1 z' + sqrt(f_ev V))^2 + f_g2s v [boost]
+    float f_ev;         // lc * c = e^{-k dt}
+    float f_scale;      // c / 2                   (Poisson-mixture path)
     float k, ktheta_T, inv_sigma;
     int   fast;         // 1: d - 1/2 > 0, chi-square split; 0: Poisson-mixture path
 };
@@ -126,7 +127,7 @@ __device__ __forceinline__ float poisson_inversion(float mu, float u)
 //   the shape<1 boost uniform is spliced from the bits those mantissas leave over: wa[8:0] : wb[8:0] : wc[4:0]
 // Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp: accept iff v1 > 0 and
 //   log2 u < (x^2/2 + d (1 - v)) log2 e + d log2 v          (the exact test; no squeeze, hence no divergence)
-// Returns accept; zp = Z / c0, g2 = 2 Gamma(a).
+// Returns accept; zp = Z / c0, g2 = c Gamma(a) (the gamma term already scaled to V').
 __device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t wc, const EmPoint &pc, float &zp, float &g2)
 {
     const float rad = sqrt_approx(-lg2_approx(u01_open(wa)));
@@ -136,9 +137,9 @@ __device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t
     const float v1 = fmaf(pc.f_c, xp, 1.0f);
     const float v = v1 * v1 * v1;
     const float x2 = xp * xp;
-    float rhs = fmaf(x2, pc.f_h, pc.f_dl * (1.0f - v));
+    float rhs = fmaf(x2, pc.f_h, fmaf(-pc.f_dl, v, pc.f_dl));
     rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
-    g2 = pc.f_g2 * v;
+    g2 = pc.f_g2s * v;
     if (pc.inv_a != 0.0f) {                                      // shape < 1 boost: Gamma(a) = Gamma(a+1) U^(1/a)
         const uint32_t m = ((wa & 0x1ffu) << 14) | ((wb & 0x1ffu) << 5) | (wc & 0x1fu);
         const float ub = __uint_as_float(m | 0x3f800000u) - 0.99999994f;
@@ -173,7 +174,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
     asm volatile("" : "+r"(path_hi));                       // computed once, not re-derived from blockIdx in the loop
     const uint32_t stream = L.call0 + (uint32_t)point;      // ctr.y: one stream per compute() call / point
 
-    float V = L.v0, vI = 0.0f, S = 0.0f;
+    float V = L.v0, acc = 0.0f, S = 0.0f;                  // acc = V_1 + ... + V_n so far
     {
         // counter = (trial block, stream, path_lo, path_hi): everything but the first word is fixed for this path
         const PhiloxPathInv inv = philox_path_invariants(stream, path_lo, L.keys);
@@ -197,11 +198,10 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                 for (int j = 0; j < 4; ++j) {
                     float zp, g2;
                     const bool ok = em_fast_trial(w[3 * j], w[3 * j + 1], w[3 * j + 2], pc, zp, g2);
-                    const float t = fmaf(1.17741002f, zp, sqrt_approx(pc.two_lc * V));
-                    const float gsum = fmaf(t, t, g2);          // = 2 V'/c
+                    const float t = fmaf(pc.f_t1, zp, sqrt_approx(pc.f_ev * V));
+                    const float Vn = fmaf(t, t, g2);            // = (c/2) ((Z + sqrt(2 l))^2 + 2 Gamma(a))
                     if (ok && step < L.N) {
-                        const float Vn = __fmul_rn(pc.f_scale, gsum);
-                        vI = __fadd_rn(vI, __fadd_rn(V, Vn));   // trapezoid sum, NMCH_EM.cu:243
+                        acc = __fadd_rn(acc, Vn);
                         V = Vn;
                         ++step;
                     }
@@ -248,7 +248,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                     float gam;
                     if (mt_trial(x, u01_open(wg.z), md, mc, gam)) {
                         const float Vn = __fmul_rn(pc.f_scale, 2.0f * gam * boost);   // f_scale = c / 2
-                        vI = __fadd_rn(vI, __fadd_rn(V, Vn));
+                        acc = __fadd_rn(acc, Vn);
                         V = Vn;
                         ++step;
                         have_np = false;
@@ -260,7 +260,8 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         const U4 w = next_block(blk);
         float z, unused;
         box_muller_fast(w.x, w.y, z, unused);
-        vI *= L.half_dt;
+        // trapezoid sum of NMCH_EM.cu:243,  sum_i (V_i + V_{i+1}) = 2 (V_1 + ... + V_N) + V_0 - V_N,  times dt / 2
+        const float vI = fmaf(2.0f, acc, L.v0 - V) * L.half_dt;
         float m = pc.inv_sigma * (V - L.v0 - pc.ktheta_T + pc.k * vI);
         m = fmaf(L.rho, m, fmaf(-0.5f, vI, L.lnS0_rT));
         S = __expf(fmaf(sqrt_approx(L.one_m_rho2 * vI), z, m));
@@ -473,7 +474,6 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
     EmPoint pt{};
     pt.scale = (float)(sigma * sigma * om / (2.0 * k));
     pt.lc = (float)(2.0 * k * e / (sigma * sigma * om));
-    pt.two_lc = 2.0f * pt.lc;
     pt.d = (float)(2.0 * k * theta / (sigma * sigma));
     double a = 2.0 * k * theta / (sigma * sigma) - 0.5;
     pt.a = (float)a;
@@ -491,7 +491,10 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
     pt.f_c = (float)(pt.mt_c * c0);
     pt.f_h = (float)(0.5 * c0 * c0 * log2e);
     pt.f_dl = (float)(pt.mt_d * log2e);
-    pt.f_g2 = 2.0f * pt.mt_d;
+    const double cc = sigma * sigma * om / (2.0 * k);
+    pt.f_g2s = (float)(pt.mt_d * cc);
+    pt.f_t1 = (float)(c0 * std::sqrt(0.5 * cc));
+    pt.f_ev = (float)e;
     pt.f_scale = 0.5f * pt.scale;
     pt.k = kf;
     pt.ktheta_T = (float)(k * theta * (double)p.T);
@@ -502,8 +505,8 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
 
 static bool em_point_finite(const EmPoint &pt)
 {
-    const float v[] = {pt.scale, pt.two_lc, pt.lc, pt.d, pt.a, pt.mt_d, pt.mt_c, pt.inv_a, pt.f_c, pt.f_h, pt.f_dl,
-                       pt.f_g2, pt.f_scale, pt.k, pt.ktheta_T, pt.inv_sigma};
+    const float v[] = {pt.scale, pt.lc, pt.d, pt.a, pt.mt_d, pt.mt_c, pt.inv_a, pt.f_c, pt.f_h, pt.f_dl,
+                       pt.f_g2s, pt.f_t1, pt.f_ev, pt.f_scale, pt.k, pt.ktheta_T, pt.inv_sigma};
     for (float x : v)
         if (!std::isfinite(x)) return false;
     return pt.scale > 0.0f && pt.lc > 0.0f;
