@@ -336,7 +336,7 @@ def main():
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj):
             try:
-                traffic = json.load(open(tj)).get(args.method)
+                traffic = json.load(open(tj)).get("fe_dense" if (args.method == "fe" and args.rng == "dense") else args.method)
             except Exception:
                 traffic = None
         line = {
