@@ -166,11 +166,28 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3):
                 out[rng]["ours_same_draws"] = {"value": units / (best * 1e-3), "exec_ms": best, "max_rel_diff_E": rel}
             except Exception as ex:  # noqa: BLE001
                 out[rng]["ours_same_draws"] = {"error": str(ex)[:200]}
+            if rng == "xorwow" and method == "fe":
+                # the same integer draws through the native fast-math step (opt-in NMCH_RNG_XORWOW_FAST)
+                try:
+                    with E.Engine(NTPB=512, NB=n // 512, N=N, rng=E.RNG_XORWOW_FAST, **README) as eng:
+                        eng.init(1234)
+                        eng.compute()
+                        ours = [eng.compute() for _ in range(repeat)]
+                    rel = max(abs(o_.mean - r_["E"]) / abs(r_["E"]) for o_, r_ in zip(ours, rows))
+                    relv = max(abs(o_.variance - (r_["E2"] - r_["E"] ** 2)) / (r_["E2"] - r_["E"] ** 2)
+                               for o_, r_ in zip(ours, rows))
+                    best = min(o_.exec_ms for o_ in ours)
+                    out[rng]["ours_same_stream_fast"] = {"value": units / (best * 1e-3), "exec_ms": best,
+                                                         "max_rel_diff_E": rel, "max_rel_diff_var": relv}
+                except Exception as ex:  # noqa: BLE001
+                    out[rng]["ours_same_stream_fast"] = {"error": str(ex)[:200]}
         except Exception as ex:  # noqa: BLE001
             out[rng] = {"error": str(ex)[:200]}
     out["what"] = (f"reference NMCH_{method.upper()}_K3_MM<rng> (unmodified sources, -O3 -arch=sm_100), 512 x {n // 512} "
                    f"paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); unit as `unit`; ours_same_draws = "
-                   "this engine in the draw-compatible mode for that tag, same seed and calls (relative difference of E[X])")
+                   "this engine in the draw-compatible mode for that tag, same seed and calls (relative difference of E[X]); "
+                   "ours_same_stream_fast = the same XORWOW integer draws through the native fast-math step "
+                   "(NMCH_RNG_XORWOW_FAST)")
     return out
 
 

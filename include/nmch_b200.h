@@ -45,9 +45,15 @@ typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
  *   PHILOX_DENSE   opt-in FE throughput mode: the same Philox4x32-10 blocks cut into THREE (23-bit radius, 19-bit
  *                  angle) draws instead of two word pairs, i.e. a third fewer generator multiplies per step.  Statistically
  *                  equivalent, NOT word-compatible with cuRAND's per-step layout (checked against a restatement of its
- *                  own mapping and against the semi-analytic price) */
+ *                  own mapping and against the semi-analytic price)
+ *   XORWOW_FAST    opt-in FE mode on the reference's default stream: the SAME cuRAND-XORWOW integer draws per path
+ *                  as XORWOW_COMPAT (same seed scramble, subsequence skip-ahead and continuation across compute()
+ *                  calls), pushed through the native fast-math step (23-bit uniforms, MUFU transforms) instead of
+ *                  cuRAND's IEEE transforms.  Prices agree with the reference's CUDA build on identical seeds to
+ *                  ~1e-6 relative (the 1e-5 tolerance of the XORWOW-compatible mode) at 2.5x its speed; per-path
+ *                  values agree to ~1e-4, not to the last bits -- use XORWOW_COMPAT for draw-for-draw validation */
 typedef enum { NMCH_RNG_PHILOX = 0, NMCH_RNG_XORWOW_COMPAT = 1, NMCH_RNG_PHILOX_COMPAT = 2,
-               NMCH_RNG_MRG32K3A_COMPAT = 3, NMCH_RNG_PHILOX_DENSE = 4 } nmch_rng;
+               NMCH_RNG_MRG32K3A_COMPAT = 3, NMCH_RNG_PHILOX_DENSE = 4, NMCH_RNG_XORWOW_FAST = 5 } nmch_rng;
 
 /* Replaces the constructor arguments of nmch::methods::NMCH (include/NMCH/methods/NMCH.hpp:42,
  * src/NMCH/methods/NMCH.cu:6-10).  Zero in an "auto" field selects the default. */

@@ -8,7 +8,7 @@ from . import _build
 
 METHOD_FE, METHOD_EM, METHOD_QE = 0, 1, 2
 FLOOR_ABS, FLOOR_PLUS = 0, 1
-RNG_PHILOX, RNG_XORWOW_COMPAT, RNG_PHILOX_COMPAT, RNG_MRG32K3A_COMPAT, RNG_PHILOX_DENSE = 0, 1, 2, 3, 4
+RNG_PHILOX, RNG_XORWOW_COMPAT, RNG_PHILOX_COMPAT, RNG_MRG32K3A_COMPAT, RNG_PHILOX_DENSE, RNG_XORWOW_FAST = 0, 1, 2, 3, 4, 5
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4
 

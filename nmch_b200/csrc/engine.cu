@@ -86,15 +86,17 @@ int pick_paths_per_thread(const nmch_engine *e, int n_points)
     return 1;
 }
 
-FePoint fold_fe_point(const nmch_params_t &p, float k, float theta, float sigma)
+FePoint fold_fe_point(const nmch_params_t &p, float k, float theta, float sigma, bool exact_v = false)
 {
-    const float dt = p.T / (float)p.N;                       // NMCH.cu:9
-    const float c0 = 1.17741002f;                            // sqrt(2 ln 2)
+    // dt as the reference forms it (float, NMCH.cu:9); everything derived from it in double, rounded once
+    const double dt = (double)(p.T / (float)p.N);
+    const double c0 = 1.1774100225154747;                    // sqrt(2 ln 2)
     FePoint pt;
-    pt.va = 1.0f - k * dt;
-    pt.vb = k * theta * dt;
-    pt.vs = sigma * sqrtf(dt) * c0;
-    pt.pad = 0.0f;
+    pt.va = (float)(1.0 - (double)k * dt);
+    pt.kdt = (float)((double)k * dt);
+    // folded map V*va + vb: keep its fixed point at theta although va is rounded; exact map V - kdt*V + vb: plain k theta dt
+    pt.vb = exact_v ? (float)((double)k * (double)theta * dt) : (float)((double)theta * (1.0 - (double)pt.va));
+    pt.vs = (float)((double)sigma * std::sqrt(dt) * c0);
     return pt;
 }
 
@@ -102,7 +104,7 @@ void fill_fe_launch(const nmch_engine *e, FeLaunch &L, int n_points, int blocks_
 {
     const nmch_params_t &p = e->p;
     const float dt = p.T / (float)p.N;
-    const float c0 = 1.17741002f;
+    const double c0 = 1.1774100225154747;                    // sqrt(2 ln 2)
     L.keys = philox_expand_keys(e->seed);
     L.first_path = e->first_path;
     L.n_local = e->n_local;
@@ -118,15 +120,15 @@ void fill_fe_launch(const nmch_engine *e, FeLaunch &L, int n_points, int blocks_
     L.S0 = p.S_0;
     L.v0 = p.v_0;
     L.K = p.S_0;                                             // at the money, NMCH.cu:7
-    L.crdt = 1.0f + p.r * dt;
-    L.zr = p.rho * sqrtf(dt) * c0;
-    L.zc = sqrtf(1.0f - p.rho * p.rho) * sqrtf(dt) * c0;
+    L.rdt = p.r * dt;
+    L.zr = (float)((double)p.rho * std::sqrt((double)dt) * c0);
+    L.zc = (float)(std::sqrt(1.0 - (double)p.rho * (double)p.rho) * std::sqrt((double)dt) * c0);
     L.r = p.r;
     L.rho = p.rho;
     L.dt = dt;
     L.sqrt_dt = sqrtf(dt);                                   // NMCH_FE.cu:152
     L.sqrt_rho = sqrtf(1 - p.rho * p.rho);                   // NMCH_FE.cu:153
-    L.pt0 = fold_fe_point(p, p.k, p.theta, p.sigma);
+    L.pt0 = fold_fe_point(p, p.k, p.theta, p.sigma, p.rng == NMCH_RNG_XORWOW_FAST);
     L.raw0 = RawPoint{p.k, p.theta, p.sigma, 0.0f};
 }
 
@@ -235,6 +237,23 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                 CU_TRY(launch_fe_dense(L, p.floor, P, d_pts, rb, S_out, V_out, stream, &e->kinfo));
             else
                 CU_TRY(launch_fe_philox(L, p.floor, P, threads, exact, d_pts, rb, S_out, V_out, stream, &e->kinfo));
+        } else if (p.rng == NMCH_RNG_XORWOW_FAST) {
+            // the XORWOW stream of the compat mode, the folded constants of the native mode
+            const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
+            if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
+            fill_fe_launch(e, L, n_points, (int)bpp, 1);
+            int rc = ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(FePoint));
+            if (rc) return rc;
+            const FePoint *d_pts = nullptr;
+            if (!own) {
+                std::vector<FePoint> pts(n_points);
+                for (int i = 0; i < n_points; ++i) pts[i] = fold_fe_point(p, k[i], theta[i], sigma[i], true);
+                CU_TRY(cudaMemcpyAsync(e->d_points, pts.data(), pts.size() * sizeof(FePoint), cudaMemcpyHostToDevice, stream));
+                CU_TRY(cudaStreamSynchronize(stream));
+                d_pts = static_cast<const FePoint *>(e->d_points);
+            }
+            ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
+            CU_TRY(launch_fe_xorwow_fast(L, p.floor, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
         } else {
             const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
             if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
@@ -306,9 +325,11 @@ int nmch_engine_create(const nmch_params_t *params, nmch_engine_t **out)
     if (p.method == NMCH_METHOD_QE && p.rng != NMCH_RNG_PHILOX)
         return fail(NMCH_ERR_ARG, "the QE scheme has no reference counterpart to be draw-compatible with: use rng = PHILOX");
     if (p.floor != NMCH_FLOOR_ABS && p.floor != NMCH_FLOOR_PLUS) return fail(NMCH_ERR_ARG, "unknown floor");
-    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_PHILOX_DENSE) return fail(NMCH_ERR_ARG, "unknown rng mode");
+    if (p.rng < NMCH_RNG_PHILOX || p.rng > NMCH_RNG_XORWOW_FAST) return fail(NMCH_ERR_ARG, "unknown rng mode");
     if (p.rng == NMCH_RNG_PHILOX_DENSE && p.method != NMCH_METHOD_FE)
         return fail(NMCH_ERR_ARG, "PHILOX_DENSE is an FE stream mode");
+    if (p.rng == NMCH_RNG_XORWOW_FAST && p.method != NMCH_METHOD_FE)
+        return fail(NMCH_ERR_ARG, "XORWOW_FAST is an FE stream mode (EM on the XORWOW tag: XORWOW_COMPAT)");
     unsigned long long n = p.n_paths;
     if (n == 0) {
         if (p.NTPB <= 0 || p.NB <= 0) return fail(NMCH_ERR_ARG, "NTPB and NB must be positive");
@@ -373,7 +394,7 @@ static int engine_init_impl(nmch_engine_t *e, unsigned long long seed)
     e->draw_offset = 0;
     e->em_calls = 0;
     e->threads = e->p.block_threads ? e->p.block_threads : 128;
-    if (e->p.rng == NMCH_RNG_XORWOW_COMPAT) {
+    if (e->p.rng == NMCH_RNG_XORWOW_COMPAT || e->p.rng == NMCH_RNG_XORWOW_FAST) {
         const size_t n = (size_t)e->n_local;
         CU_TRY(xorwow_tables_create(&e->xtab));
         uint32_t *base = nullptr;

@@ -11,7 +11,7 @@
 //   * u32 -> float by bit splicing (ALU pipe, no I2F on the XU pipe)
 //   * Box-Muller with MUFU.LG2 / MUFU.SIN / MUFU.COS and ONE MUFU.SQRT shared with the SDE:
 //       sqrt(V)*sqrt(-2 ln u) = c0 * sqrt(-V * lg2 u),  c0 = sqrt(2 ln 2) folded into host constants
-//   * S' = S * (1 + r dt + q sin * zr + q cos * zc),  V' = g(V*va + vb + q sin * vs)
+//   * S' = S + S * (r dt + q sin * zr + q cos * zc),  V' = g(V*va + vb + q sin * vs)
 //   state (S, V, counters) stays in registers for all N steps: zero HBM traffic in the loop.
 #include "compat_math.cuh"
 #include "kernels.cuh"
@@ -21,8 +21,13 @@ namespace nmchb {
 // ------------------------------------------------------------------------------------------
 // native Philox kernel
 // ------------------------------------------------------------------------------------------
-template <int FLOOR>
-__device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, uint32_t wb, float crdt,
+// PRECISE_V: V' = g(V - kdt*V + (vb + q sin * vs)) with the product rounded once, instead of the folded
+// V*va + vb + ... -- one more FP32 operation.  The folded va = 1 - k*dt carries a rounding error of up to 3e-8, i.e. a
+// relative error of up to 3e-8 / (k dt) in the mean-reversion speed; fold_fe_point compensates vb so that the
+// long-run level stays theta, which is all the 3-standard-error modes need.  The XORWOW_FAST mode promises 1e-5
+// against the reference on identical draws and takes the exact form.
+template <int FLOOR, bool PRECISE_V = false>
+__device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, uint32_t wb, float rdt,
                                                float zr, float zc, const FePoint &pc)
 {
     const float f1 = bits_to_1_2(wa);
@@ -33,11 +38,16 @@ __device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, 
     const float ang = f2 * 6.2831855f;                // [2pi, 4pi): same sine/cosine as [0, 2pi)
     const float gs = q * sin_approx(ang);
     const float gc = q * cos_approx(ang);
-    float m = fmaf(gs, zr, crdt);
-    m = fmaf(gc, zc, m);
-    S *= m;
-    float vn = fmaf(V, pc.va, pc.vb);
-    vn = fmaf(gs, pc.vs, vn);
+    float m = fmaf(gs, zr, rdt);                      // relative increment; S' = S + S*m keeps r*dt at full precision
+    m = fmaf(gc, zc, m);                              // (a folded 1 + r*dt would round by up to 6e-8 every step, a
+    S = fmaf(S, m, S);                                //  systematic drift of N * 6e-8 on S_T)
+    float vn;
+    if constexpr (PRECISE_V) {
+        vn = fmaf(-pc.kdt, V, V) + fmaf(gs, pc.vs, pc.vb);
+    } else {
+        vn = fmaf(V, pc.va, pc.vb);
+        vn = fmaf(gs, pc.vs, vn);
+    }
     V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
 }
 
@@ -54,7 +64,7 @@ __device__ __forceinline__ void fe_step_any(float &S, float &V, uint32_t wa, uin
         // for EXACT launches the point record carries the raw (k, theta, sigma) in (va, vb, vs)
         fe_step_compat<FLOOR>(S, V, gx, gy, L.r, pc.va, L.rho, pc.vb, pc.vs, L.dt, L.sqrt_dt, L.sqrt_rho);
     } else {
-        fe_step_native<FLOOR>(S, V, wa, wb, L.crdt, L.zr, L.zc, pc);
+        fe_step_native<FLOOR>(S, V, wa, wb, L.rdt, L.zr, L.zc, pc);
     }
 }
 
@@ -203,9 +213,9 @@ __device__ __forceinline__ void fe_step_dense(float &S, float &V, const U4 &w, i
     const float ang = f2 * 6.2831855f;
     const float gs = q * sin_approx(ang);
     const float gc = q * cos_approx(ang);
-    float m = fmaf(gs, L.zr, L.crdt);
+    float m = fmaf(gs, L.zr, L.rdt);
     m = fmaf(gc, L.zc, m);
-    S *= m;
+    S = fmaf(S, m, S);
     float vn = fmaf(V, pc.va, pc.vb);
     vn = fmaf(gs, pc.vs, vn);
     V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
@@ -454,6 +464,76 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
         xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;
         xs.v2[idx] = xw.v2; xs.v3[idx] = xw.v3; xs.v4[idx] = xw.v4;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// XORWOW stream + native step (opt-in mode NMCH_RNG_XORWOW_FAST): the reference's default generator, and therefore
+// the same integer draws per path as its CUDA build on the same seed, but the native arithmetic -- bit-spliced
+// 23-bit uniforms, MUFU Box-Muller sharing its square root with the SDE, folded constants.  XORWOW needs no
+// multiplies (8 ALU-pipe operations per draw), so the FMA pipe that binds the Philox kernels is left to the 11 FP32
+// operations of the step: 37.8 cycles per warp-step.  One path per thread (six state words in registers), the step
+// loop unrolled by five so that the rotation of the five xorshift words costs no moves; the points of a sweep are
+// walked inside the thread because the stream is sequential (the reference's order), state written back at the end.
+// ------------------------------------------------------------------------------------------
+template <int FLOOR>
+__global__ void __launch_bounds__(256, 8)
+fe_xorwow_fast_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ pts, XorwowState xs,
+                      ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < L.n_local;
+    CompatXorwow xw{};
+    if (valid) {
+        xw.d = xs.d[idx]; xw.v0 = xs.v0[idx]; xw.v1 = xs.v1[idx];
+        xw.v2 = xs.v2[idx]; xw.v3 = xs.v3[idx]; xw.v4 = xs.v4[idx];
+    }
+    for (int point = 0; point < L.n_points; ++point) {
+        const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
+        float S = L.S0, V = L.v0;
+        if (valid) {
+#pragma unroll 5
+            for (int n = 0; n < L.N; ++n) {
+                const uint32_t a = xw.next();                  // first draw -> radius, second -> angle, x pairs with sin:
+                const uint32_t b = xw.next();                  // curand_normal2's order (curand_normal.h:70-87)
+                fe_step_native<FLOOR, true>(S, V, a, b, L.rdt, L.zr, L.zc, pc);
+            }
+        }
+        double pay = 0.0;
+        if (valid) {
+            pay = (double)fmaxf(0.0f, S - L.K);
+            if (S_out != nullptr && point == L.n_points - 1) {
+                S_out[idx] = S;
+                V_out[idx] = V;
+            }
+        }
+        block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x,
+                                L.blocks_per_point);
+    }
+    if (valid) {                                 // streams continue across compute() calls (NMCH_FE.cu:303)
+        xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;
+        xs.v2[idx] = xw.v2; xs.v3[idx] = xw.v3; xs.v4[idx] = xw.v4;
+    }
+}
+
+cudaError_t launch_fe_xorwow_fast(const FeLaunch &L, int floor_kind, const FePoint *d_pts, XorwowState xs,
+                                  ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
+{
+    const int threads = 256;                 // one path per thread; L.blocks_per_point is sized for this
+    dim3 grid((unsigned)L.blocks_per_point, 1, 1);
+    cudaFuncAttributes attr{};
+    cudaError_t err = cudaSuccess;
+    if (floor_kind == kFloorAbs) {
+        fe_xorwow_fast_kernel<kFloorAbs><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_xorwow_fast_kernel<kFloorAbs>);
+    } else {
+        fe_xorwow_fast_kernel<kFloorPlus><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        err = cudaFuncGetAttributes(&attr, fe_xorwow_fast_kernel<kFloorPlus>);
+    }
+    if (info)
+        *info = KernelInfo{(int)grid.x, 1, threads, 1, attr.numRegs,
+                           (int)(sizeof(FeLaunch) + sizeof(const FePoint *) + sizeof(XorwowState) + sizeof(ReduceBuffers) + 2 * sizeof(float *))};
+    const cudaError_t lerr = cudaGetLastError();
+    return lerr != cudaSuccess ? lerr : err;
 }
 
 cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,

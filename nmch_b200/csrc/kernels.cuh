@@ -8,13 +8,14 @@
 namespace nmchb {
 
 constexpr int kFloorAbs = 0, kFloorPlus = 1;
-constexpr int kRngPhilox = 0, kRngXorwowCompat = 1, kRngPhiloxCompat = 2, kRngMrgCompat = 3, kRngPhiloxDense = 4;
+constexpr int kRngPhilox = 0, kRngXorwowCompat = 1, kRngPhiloxCompat = 2, kRngMrgCompat = 3, kRngPhiloxDense = 4, kRngXorwowFast = 5;
 constexpr int kMaxTilePaths = 4096;     // native mode: first_path % kMaxTilePaths == 0 (no carry inside a tile)
 
 // Per-point constants of the native FE kernel, folded on the host (fold_fe_point):
-//   V' = g( V*va + vb + (sqrt(V)*n1)*vs ),  va = 1-k*dt, vb = k*theta*dt, vs = sigma*sqrt(dt)*sqrt(2 ln 2)
+//   V' = g( V*va + vb + (sqrt(V)*n1)*vs ),  va = 1-k*dt, vb = theta*(1-va) (= k*theta*dt up to the rounding of va, so
+//   that the long-run level of the folded map is theta exactly), vs = sigma*sqrt(dt)*sqrt(2 ln 2), kdt = k*dt
 struct FePoint {
-    float va, vb, vs, pad;
+    float va, vb, vs, kdt;
 };
 
 // Per-point raw parameters for the compat kernels (they evaluate the reference's expressions verbatim).
@@ -36,7 +37,7 @@ struct FeLaunch {
     int   blocks_per_point;
     int   tiles_per_block;
     float S0, v0, K;
-    float crdt;                         // 1 + r*dt
+    float rdt;                          // r*dt
     float zr, zc;                       // rho*sqrt(dt)*c0, sqrt(1-rho^2)*sqrt(dt)*c0, c0 = sqrt(2 ln 2)
     // compat kernels: the reference's own scalars (NMCH_FE.cu:135-153)
     float r, rho, dt, sqrt_dt, sqrt_rho;
@@ -75,6 +76,9 @@ cudaError_t launch_fe_dense(const FeLaunch &L, int floor_kind, int paths_per_thr
                             float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,
                              ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
+// XORWOW integer stream + the native fast-math step (NMCH_RNG_XORWOW_FAST); d_pts holds folded FePoint records
+cudaError_t launch_fe_xorwow_fast(const FeLaunch &L, int floor_kind, const FePoint *d_pts, XorwowState xs,
+                                  ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 
 // strike_kernels.cu: per-strike payoff / delta sums from terminal prices kept on the device
 cudaError_t launch_strike_moments(const float *d_S, unsigned long long n_local, const float *d_strikes, int n_strikes,

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import capi
 from .capi import (FLOOR_ABS, FLOOR_PLUS, METHOD_EM, METHOD_FE, METHOD_QE, RNG_MRG32K3A_COMPAT, RNG_PHILOX,  # noqa: F401
-                   RNG_PHILOX_COMPAT, RNG_PHILOX_DENSE, RNG_XORWOW_COMPAT)
+                   RNG_PHILOX_COMPAT, RNG_PHILOX_DENSE, RNG_XORWOW_COMPAT, RNG_XORWOW_FAST)
 
 
 @dataclass

@@ -38,7 +38,8 @@ class NMCH:
     _title = ""
 
     def __init__(self, NTPB, NB, T, S_0, v_0, r, k, rho, theta, sigma, N, rnd_state=PHILOX, *, compat=False,
-                 floor="abs", device=-1, first_path=0, n_local=0, n_paths=0, paths_per_thread=0):
+                 dense=False, fast=False, floor="abs", device=-1, first_path=0, n_local=0, n_paths=0,
+                 paths_per_thread=0):
         self.NTPB, self.NB, self.T, self.S_0, self.v_0, self.r = NTPB, NB, T, S_0, v_0, r
         self.k, self.rho, self.theta, self.sigma, self.N = k, rho, theta, sigma, N
         self.K = S_0                                   # NMCH.cu:7
@@ -48,10 +49,11 @@ class NMCH:
         self.price_squared = 0.0
         self.Tim_exec = 0.0
         self.Tim_init = 0.0
-        if rnd_state == XORWOW:
-            rng = _eng.RNG_XORWOW_COMPAT
-        elif rnd_state == PHILOX:
-            rng = _eng.RNG_PHILOX_COMPAT if compat else _eng.RNG_PHILOX
+        fe = self._method == _eng.METHOD_FE
+        if rnd_state == XORWOW:                        # fast: cuRAND's integer draws, native fast-math step (FE only)
+            rng = _eng.RNG_XORWOW_FAST if (fast and fe) else _eng.RNG_XORWOW_COMPAT
+        elif rnd_state == PHILOX:                      # dense: three steps per Philox block (FE only)
+            rng = _eng.RNG_PHILOX_COMPAT if compat else (_eng.RNG_PHILOX_DENSE if (dense and fe) else _eng.RNG_PHILOX)
         elif rnd_state == MRG32K3A:
             rng = _eng.RNG_MRG32K3A_COMPAT
         else:

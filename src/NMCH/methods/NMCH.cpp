@@ -62,7 +62,9 @@ void NMCH<rnd_state>::engine_init(int method, unsigned long long seed, float *ti
     p.method = method;
     p.floor = floor_plus ? NMCH_FLOOR_PLUS : NMCH_FLOOR_ABS;
     switch (traits::mode) {
-    case nmch::random::stream_mode::xorwow_compat: p.rng = NMCH_RNG_XORWOW_COMPAT; break;
+    case nmch::random::stream_mode::xorwow_compat:
+        p.rng = (xorwow_fast && method == NMCH_METHOD_FE) ? NMCH_RNG_XORWOW_FAST : NMCH_RNG_XORWOW_COMPAT;
+        break;
     case nmch::random::stream_mode::philox_compat: p.rng = NMCH_RNG_PHILOX_COMPAT; break;
     case nmch::random::stream_mode::mrg32k3a_compat: p.rng = NMCH_RNG_MRG32K3A_COMPAT; break;
     default: p.rng = philox_compat ? NMCH_RNG_PHILOX_COMPAT : (philox_dense ? NMCH_RNG_PHILOX_DENSE : NMCH_RNG_PHILOX); break;

@@ -1,7 +1,7 @@
 // nmch.cpp -- the `NMCH` command line tool: same flags, defaults, output text and exit codes as the reference
 // (src/NMCH/test/nmch.cu:49-139), host C++ over the method API.  Additive flags (defaults = reference behaviour):
 //   --g abs|plus        variance floor (README.md:37-40; the reference codes only abs)
-//   --rng philox|xorwow|philox-compat   generator tag / stream mode (reference CLI: Philox, nmch.cu:119,130)
+//   --rng philox|xorwow|philox-compat|philox-dense|xorwow-fast   generator tag / stream mode (reference CLI: Philox, nmch.cu:119,130)
 //   --gpus N            shard the paths over N GPUs, one NCCL allreduce of the moments
 //   --paths-per-thread P, --json (one machine-readable line after the report)
 #include <cstdio>
@@ -49,7 +49,8 @@ void usage(const char *argv0)
     printf("B200 engine options (actual defaults: NTPB 512, NB 512, N 1000):\n");
     printf("  --method qe        Quadratic-exponential large-step scheme (use with --N 50..100)\n");
     printf("  --g <abs|plus>     Variance floor g(.) (default: abs)\n");
-    printf("  --rng <philox|xorwow|philox-compat|philox-dense>  Stream mode (default: philox; philox-dense: fe only)\n");
+    printf("  --rng <philox|xorwow|philox-compat|philox-dense|xorwow-fast>  Stream mode (default: philox; philox-dense and\n");
+    printf("                     xorwow-fast: fe only; xorwow-fast = the reference's XORWOW draws, native fast-math step)\n");
     printf("  --gpus <int>       GPUs to shard the paths over (default: 1)\n");
     printf("  --paths-per-thread <int>  1, 2, 4 or 8 (default: auto)\n");
     printf("  --strikes <k1,k2,..>  Also price these strikes (and pathwise deltas) on a second pass of the streams\n");
@@ -64,6 +65,7 @@ int run(const Options &o)
     m.set_gpus(o.gpus);
     m.set_philox_compat(o.rng == "philox-compat");
     m.set_philox_dense(o.rng == "philox-dense");
+    m.set_xorwow_fast(o.rng == "xorwow-fast");
     m.set_paths_per_thread(o.ppt);
     m.init(o.seed);
     m.compute();
@@ -123,11 +125,12 @@ int main(int argc, char **argv)
         else if (strcmp(argv[i], "--json") == 0) o.json = true;
         else if (strcmp(argv[i], "--help") == 0) { usage(argv[0]); return 0; }
     }
-    if (o.rng != "philox" && o.rng != "xorwow" && o.rng != "philox-compat" && o.rng != "philox-dense") {
+    if (o.rng != "philox" && o.rng != "xorwow" && o.rng != "philox-compat" && o.rng != "philox-dense" &&
+        o.rng != "xorwow-fast") {
         printf("Unknown rng: %s\n", o.rng.c_str());
         return 1;
     }
-    const bool x = o.rng == "xorwow";
+    const bool x = o.rng == "xorwow" || o.rng == "xorwow-fast";
     if (o.method == "fe")
         return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(o);
     if (o.method == "em")
