@@ -390,6 +390,21 @@ def main():
                                               "statistically equivalent, not cuRAND-word-compatible; bench.py --rng dense"}
             except Exception as ex:  # noqa: BLE001
                 line["dense_mode"] = {"error": str(ex)[:200]}
+            try:                                  # the reference's default stream (XORWOW) through the native step
+                with E.Engine(NTPB=512, NB=n_per_gpu // 512, N=N, rng=E.RNG_XORWOW_FAST, device=local_rank,
+                              floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, **README) as xe:
+                    xe.init(1234)
+                    xe.compute()
+                    xms = min(xe.compute().exec_ms for _ in range(3))
+                    xinit = xe.init_ms
+                xval = units_per_gpu_step / (xms * 1e-3)
+                line["xorwow_fast_mode"] = {"value": xval, "unit": unit, "ms_per_step": xms, "init_ms": xinit,
+                                            "note": "NMCH_RNG_XORWOW_FAST: cuRAND-XORWOW integer draws (the reference's "
+                                                    "default generator, 24 B of state per path) through the native "
+                                                    "fast-math step; same-seed agreement with the reference CUDA build "
+                                                    "under reference_cuda.xorwow.ours_same_stream_fast"}
+            except Exception as ex:  # noqa: BLE001
+                line["xorwow_fast_mode"] = {"error": str(ex)[:200]}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.method, N, budget_s=args.cpu_budget_s or 12.0)
         if not args.no_reference_cuda and world == 1:
