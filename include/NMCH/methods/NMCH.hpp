@@ -37,8 +37,8 @@ public:
     void set_floor_plus(bool on) { floor_plus = on; }             // g = (.)+ instead of |.| (README.md:37-40)
     void set_gpus(int n) { gpus = n < 1 ? 1 : n; }                // shard paths over n devices + one NCCL allreduce
     void set_philox_compat(bool on) { philox_compat = on; }       // Philox tag: cuRAND-draw-compatible validation mode
-    void set_philox_dense(bool on) { philox_dense = on; }         // Philox tag, FE: 3 steps per Philox block (+15 %, own mapping)
-    void set_xorwow_fast(bool on) { xorwow_fast = on; }           // XORWOW tag, FE: cuRAND's integer draws, native fast-math step
+    void set_philox_dense(bool on) { philox_dense = on; }         // Philox tag, FE only (ignored otherwise): 3 steps per Philox block (+15 %, own mapping)
+    void set_xorwow_fast(bool on) { xorwow_fast = on; }           // XORWOW tag, FE only (ignored otherwise): cuRAND's integer draws, native fast-math step
     void set_paths_per_thread(int p) { paths_per_thread = p; }
     /* raw FP64 sums behind strike_price / price_squared, and the plain standard error of the mean */
     double get_sum_payoff() const { return sum_payoff; }

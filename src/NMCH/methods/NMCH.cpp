@@ -67,7 +67,10 @@ void NMCH<rnd_state>::engine_init(int method, unsigned long long seed, float *ti
         break;
     case nmch::random::stream_mode::philox_compat: p.rng = NMCH_RNG_PHILOX_COMPAT; break;
     case nmch::random::stream_mode::mrg32k3a_compat: p.rng = NMCH_RNG_MRG32K3A_COMPAT; break;
-    default: p.rng = philox_compat ? NMCH_RNG_PHILOX_COMPAT : (philox_dense ? NMCH_RNG_PHILOX_DENSE : NMCH_RNG_PHILOX); break;
+    default:                                                 // the FE-only opt-in streams are ignored by the other methods
+        p.rng = philox_compat ? NMCH_RNG_PHILOX_COMPAT
+                              : ((philox_dense && method == NMCH_METHOD_FE) ? NMCH_RNG_PHILOX_DENSE : NMCH_RNG_PHILOX);
+        break;
     }
     p.device = -1;
     p.paths_per_thread = paths_per_thread;

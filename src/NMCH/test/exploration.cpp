@@ -6,7 +6,7 @@
 // grid, filter 20*k*theta < sigma^2).  Additive flags:
 //   --points P          P points per axis on an evenly spaced grid computed in double (P = 20 is BASELINE configs[3])
 //   --log2-paths L      2^L paths per grid point (default: NTPB*NB = 5120)
-//   --method fe|em|both (default both)   --rng xorwow|philox|philox-compat (default xorwow, as the reference)
+//   --method fe|em|both (default both)   --rng xorwow|xorwow-fast|philox|philox-compat|philox-dense (default xorwow, as the reference)
 //   --no-filter         keep the points the reference skips      --gpus N      --N steps   --seed s
 //   --bias              extra CSV column: estimate minus the semi-analytic Heston price (input of heatmap.py)
 //   --sequential        per-point launches like the reference (per-point execution_time is then measured, not averaged)
@@ -67,6 +67,8 @@ void sweep(const char *name, const Options &o, const Grid &g)
     M m(o.NTPB, o.NB, T, S_0, v_0, r, 0.5f, rho, 0.1f, 0.3f, o.N);
     m.set_gpus(o.gpus);
     m.set_philox_compat(o.rng == "philox-compat");
+    m.set_philox_dense(o.rng == "philox-dense");      // FE-only opt-in streams: the EM leg of the sweep ignores them
+    m.set_xorwow_fast(o.rng == "xorwow-fast");
     m.init(o.seed);
     m.compute();                      // the reference's warm-up compute (exploration.cu:65-67); it advances the streams
     const int n = (int)g.k.size();
@@ -120,7 +122,7 @@ int main(int argc, char **argv)
         else if (strcmp(argv[i], "--bias") == 0) o.bias = true;
         else if (strcmp(argv[i], "--sequential") == 0) o.sequential = true;
         else if (strcmp(argv[i], "--help") == 0) {
-            printf("Usage: %s [--points P] [--log2-paths L] [--method fe|em|both] [--rng xorwow|philox|philox-compat]\n"
+            printf("Usage: %s [--points P] [--log2-paths L] [--method fe|em|both] [--rng xorwow|xorwow-fast|philox|philox-compat|philox-dense]\n"
                    "          [--no-filter] [--gpus N] [--N steps] [--seed s] [--bias] [--sequential]\n", argv[0]);
             return 0;
         } else {
@@ -130,8 +132,11 @@ int main(int argc, char **argv)
     }
     if (o.log2_paths >= 9) { o.NTPB = 512; o.NB = 1 << (o.log2_paths - 9); }
     const Grid g = make_grid(o);
-    const bool x = o.rng == "xorwow";
-    if (!x && o.rng != "philox" && o.rng != "philox-compat") { printf("Unknown rng: %s\n", o.rng.c_str()); return 1; }
+    const bool x = o.rng == "xorwow" || o.rng == "xorwow-fast";
+    if (!x && o.rng != "philox" && o.rng != "philox-compat" && o.rng != "philox-dense") {
+        printf("Unknown rng: %s\n", o.rng.c_str());
+        return 1;
+    }
     printf(o.bias ? "method, k, theta, sigma, execution_time, err, bias\n" : "method, k, theta, sigma, execution_time, err\n");
     if (o.method == "fe" || o.method == "both") {
         if (x) sweep<NMCH_FE_K3_MM<curandStateXORWOW_t>>("fe", o, g);

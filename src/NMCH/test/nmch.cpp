@@ -130,6 +130,10 @@ int main(int argc, char **argv)
         printf("Unknown rng: %s\n", o.rng.c_str());
         return 1;
     }
+    if ((o.rng == "philox-dense" || o.rng == "xorwow-fast") && o.method != "fe") {
+        printf("--rng %s is a forward-Euler stream mode (use --method fe)\n", o.rng.c_str());
+        return 1;
+    }
     const bool x = o.rng == "xorwow" || o.rng == "xorwow-fast";
     if (o.method == "fe")
         return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(o);

@@ -79,6 +79,25 @@ def test_nmch_xorwow_tag_matches_reference_binary():
 
 
 @pytest.mark.gpu
+def test_nmch_opt_in_stream_modes():
+    """--rng xorwow-fast: the reference's draws, native arithmetic (same price as the reference binary to 1e-5);
+    --rng philox-dense: own mapping (statistical agreement); both are FE-only and say so for --method em."""
+    from oracle import oracle as o
+    j = json.loads(run(NMCH, "--rng", "xorwow-fast", "--NB", 128, "--N", 300, "--json").stdout.splitlines()[-1])
+    if os.path.exists(o.REF_HARNESS_PATH):
+        ref = json.loads(run(o.REF_HARNESS_PATH, "--method", "fe", "--rng", "xorwow", "--NB", 128, "--N", 300).stdout.splitlines()[0])
+        assert abs(j["E"] - ref["E"]) / ref["E"] < 1e-5
+    c = json.loads(run(NMCH, "--rng", "xorwow", "--NB", 128, "--N", 300, "--json").stdout.splitlines()[-1])
+    assert abs(j["E"] - c["E"]) / c["E"] < 1e-5 and j["rng"] == "xorwow-fast"
+    d = json.loads(run(NMCH, "--rng", "philox-dense", "--NB", 2048, "--N", 300, "--json").stdout.splitlines()[-1])
+    p = json.loads(run(NMCH, "--rng", "philox", "--NB", 2048, "--N", 300, "--json").stdout.splitlines()[-1])
+    assert abs(d["E"] - p["E"]) < 3 * np.hypot(d["std_error"], p["std_error"])
+    for mode in ("xorwow-fast", "philox-dense"):                   # FE-only stream modes
+        r = run(NMCH, "--method", "em", "--rng", mode, "--NB", 8, "--N", 10)
+        assert r.returncode == 1 and "forward-Euler stream mode" in r.stdout
+
+
+@pytest.mark.gpu
 def test_exploration_default_run_is_the_reference_sweep():
     from oracle import oracle as o
     r = run(EXPL, "--N", 40)

@@ -26,7 +26,7 @@ def test_group_of_one_equals_engine(method):
     assert a.sum_payoff == b.sum_payoff and a.sum_payoff_sq == b.sum_payoff_sq and b.n_paths == 512 * 64
 
 
-@pytest.mark.parametrize("method,rng", [(0, 0), (0, 1), (1, 0)])
+@pytest.mark.parametrize("method,rng", [(0, 0), (0, 1), (1, 0), (0, 4), (0, 5)])
 def test_group_shards_add_up(method, rng):
     from nmch_b200 import Engine, Group
     n = _ngpu()
