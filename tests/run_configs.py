@@ -90,13 +90,23 @@ def main():
             e.init(1234)
             first = e.compute()
             out["xorwow_compat"] = {"first_call": stats(first), "init_ms": e.init_ms}
+        for name, mode in (("philox_dense", E.RNG_PHILOX_DENSE), ("xorwow_fast", E.RNG_XORWOW_FAST)):   # opt-in FE streams
+            with E.Engine(NTPB=512, NB=n // 512, N=1000, rng=mode) as e:
+                e.init(1234)
+                first = e.compute()
+                m = best_of(e)
+                init_ms = e.init_ms
+            out[name] = {"first_call": stats(first), "best_exec_ms": m.exec_ms, "init_ms": init_ms,
+                         "path_steps_per_s": n * 1000 / (m.exec_ms * 1e-3)}
         out["reference_cuda_xorwow"] = ref_cuda("fe", "xorwow", n // 512)
         out["reference_cuda_philox"] = ref_cuda("fe", "philox", n // 512)
         r = out["reference_cuda_xorwow"]
         if r and "first_call" in r:
-            c, f = out["xorwow_compat"]["first_call"], r["first_call"]
-            out["compat_vs_reference"] = {"rel_E": abs(c["E"] - f["E"]) / f["E"],
-                                          "rel_var": abs((c["E2"] - c["E"] ** 2) - (f["E2"] - f["E"] ** 2)) / (f["E2"] - f["E"] ** 2)}
+            f = r["first_call"]
+            for key, mine in (("compat_vs_reference", "xorwow_compat"), ("xorwow_fast_vs_reference", "xorwow_fast")):
+                c = out[mine]["first_call"]
+                out[key] = {"rel_E": abs(c["E"] - f["E"]) / f["E"],
+                            "rel_var": abs((c["E2"] - c["E"] ** 2) - (f["E2"] - f["E"] ** 2)) / (f["E2"] - f["E"] ** 2)}
         rep["c2"] = out
         print("c2", json.dumps(out), flush=True)
 
@@ -130,21 +140,23 @@ def main():
         k, th, sg = (np.array(x, np.float32) for x in zip(*pts))
         n = 1 << args.c4_log2_paths
         out = {"points": len(k), "grid": f"{P}^3 with the reference's 20*k*theta<sigma^2 skip", "paths_per_point": n}
-        for name, method in (("fe", E.METHOD_FE), ("em", E.METHOD_EM)):
-            with E.Group(ngpu, NTPB=512, NB=n // 512, N=1000, method=method) as g:
+        for name, method, mode in (("fe", E.METHOD_FE, E.RNG_PHILOX), ("em", E.METHOD_EM, E.RNG_PHILOX),
+                                   ("fe_philox_dense", E.METHOD_FE, E.RNG_PHILOX_DENSE),
+                                   ("fe_xorwow_fast", E.METHOD_FE, E.RNG_XORWOW_FAST)):
+            with E.Group(ngpu, NTPB=512, NB=n // 512, N=1000, method=method, rng=mode) as g:
                 g.init(1234)
                 t0 = time.perf_counter()
                 res = g.explore(k, th, sg)
                 wall = time.perf_counter() - t0
             ms = res[0].exec_ms
-            units = len(k) * n * (1000 if name == "fe" else 1)
+            units = len(k) * n * (1000 if name.startswith("fe") else 1)
             z = []
             for i in np.linspace(0, len(k) - 1, 12).astype(int):
                 want = o.heston_call(kappa=float(k[i]), theta=float(th[i]), sigma=float(sg[i]))
                 z.append({"k": float(k[i]), "theta": float(th[i]), "sigma": float(sg[i]), "E": res[i].mean, "heston": want,
                           "z": (res[i].mean - want) / res[i].std_error})
             out[name] = {"launch_ms": ms, "wall_s": wall, "gpus": ngpu,
-                         ("path_steps_per_s" if name == "fe" else "paths_per_s"): units / (ms * 1e-3), "sample_points": z}
+                         ("path_steps_per_s" if name.startswith("fe") else "paths_per_s"): units / (ms * 1e-3), "sample_points": z}
             print("c4", name, json.dumps({k2: v for k2, v in out[name].items() if k2 != "sample_points"}), flush=True)
         rep["c4"] = out
 
