@@ -16,6 +16,7 @@
 //   compared with the reference's CUDA build on identical seeds.
 #include <curand_kernel.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "compat_math.cuh"
@@ -43,6 +44,7 @@ struct EmPoint {
     float f_scale;      // c / 2                   (Poisson-mixture path)
     float k, ktheta_T, inv_sigma;
     int   fast;         // 1: d - 1/2 > 0, chi-square split; 0: Poisson-mixture path
+    int   index;        // position of the point in the caller's list (stream id, result slot): launches group points by kind
 };
 
 struct EmLaunch {
@@ -99,14 +101,17 @@ __device__ __forceinline__ bool ptrs_trial(float mu, float u_raw, float v, float
     const float smu = sqrt_approx(mu);
     const float b = fmaf(2.53f, smu, 0.931f);
     const float a = fmaf(0.02483f, b, -0.059f);
-    const float inv_alpha = 1.1239f + 1.1328f / (b - 3.4f);
-    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    // the hat's constants may be approximate (MUFU.RCP, 1e-7): they only shape the proposal and enter the exact test
+    // below consistently; the target pmf itself is evaluated with IEEE division and logf
+    const float inv_alpha = fmaf(1.1328f, rcp_approx(b - 3.4f), 1.1239f);
+    const float vr = fmaf(-3.6224f, rcp_approx(b - 2.0f), 0.9277f);
     const float u = u_raw - 0.5f;
     const float us = 0.5f - fabsf(u);
-    k = floorf(fmaf(2.0f * a / us + b, u, mu + 0.43f));
+    const float inv_us = rcp_approx(us);
+    k = floorf(fmaf(fmaf(2.0f * a, inv_us, b), u, mu + 0.43f));
     if (us >= 0.07f && v <= vr) return true;
     if (k < 0.0f || (us < 0.013f && v > us)) return false;
-    return logf(v * inv_alpha / (a / (us * us) + b)) <= poisson_log_pmf(k, mu);
+    return logf(v * inv_alpha * rcp_approx(fmaf(a * inv_us, inv_us, b))) <= poisson_log_pmf(k, mu);
 }
 
 // Poisson by inversion (mu < 10): exact, one uniform.
@@ -157,13 +162,16 @@ __device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t
 #endif
 constexpr int kEmThreads = NMCHB_EM_THREADS;
 
-template <bool MIXED>
+// SLOW = false: the chi-square split (points with d > 1/2); SLOW = true: the Poisson mixture (d <= 1/2).  A sweep whose
+// grid holds both kinds is two launches, each over its own points (pts[] is grouped by kind on the host and carries the
+// caller's index): one loop per kernel keeps both free of spills, and no block pays for the other kind's code.
+template <bool SLOW>
 __global__ void __launch_bounds__(kEmThreads, NMCHB_EM_MINB)
 em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__ pts, ReduceBuffers rb,
                  float *__restrict__ S_out, float *__restrict__ V_out)
 {
-    const int point = blockIdx.y;
-    const EmPoint pc = (pts != nullptr) ? pts[point] : L.pt0;
+    const EmPoint pc = (pts != nullptr) ? pts[blockIdx.y] : L.pt0;
+    const int point = pc.index;
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
     // first_path is a multiple of 4096 (checked at create): the high counter word is the same for the whole
@@ -184,7 +192,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         };
         uint32_t blk = 0;
         int step = valid ? 0 : L.N;                          // lanes past the end of the shard take part in the votes only
-        if (!MIXED || pc.fast) {
+        if constexpr (!SLOW) {
             // chi-square split.  A trial needs four 23-bit fields (radius, angle, accept-test uniform, shape<1 boost
             // uniform) = 92 bits, so FOUR trials share THREE Philox blocks: trial j takes words 3j..3j+2 (em_fast_trial).
             // The generator multiplies are the scarce resource, a quarter of them is saved.
@@ -208,9 +216,10 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                 }
             }
         } else {
-            // Poisson mixture (d <= 1/2): one trial per iteration on a fresh block.  First a Poisson draw, then, on a
-            // block of its own, one Marsaglia-Tsang trial for Gamma(d + N).  A lane that already holds N uses this
-            // iteration's block for the gamma trial directly, so a gamma retry never re-draws (and never biases) N.
+            // Poisson mixture (d <= 1/2): per iteration ONE Philox block feeds a Poisson trial (two 23-bit uniforms)
+            // and, from disjoint bits of the same block, one Marsaglia-Tsang trial for Gamma(d + N) (23-bit radius,
+            // 19-bit angle, 23-bit accept uniform, 17-bit boost uniform: 128 bits in all).  A lane that already holds
+            // N skips the Poisson part, so a gamma retry never re-draws (and never biases) N.
             // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive),
             // so the loop terminates; the cap is a belt against a hang: a path that exhausts it ends early and poisons
             // the sum with NaN instead of stalling the GPU.  (The split path is not taxed with it.)
@@ -220,8 +229,6 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
             while (step < L.N) {
                 if (blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
                 const U4 w = next_block(blk++);
-                U4 wg = w;
-                bool gamma_now = have_np;
                 if (!have_np) {
                     const float mu = pc.lc * V;
                     if (mu < 10.0f) {
@@ -230,23 +237,22 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
                     } else {
                         have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), np);
                     }
-                    if (have_np) {
-                        wg = next_block(blk++);
-                        gamma_now = true;
-                    }
                 }
-                if (gamma_now) {
-                    float x, unused;
-                    box_muller_fast(wg.x, wg.y, x, unused);
+                if (have_np) {
+                    const uint32_t a19 = ((w.x & 0x1ffu) << 10) | ((w.y & 0x1ffu) << 1) | ((w.z >> 8) & 1u);
+                    const float rad = sqrt_approx(-1.38629436f * lg2_approx(u01_open(w.z)));      // sqrt(-2 ln u)
+                    const float x = rad * sin_approx(__uint_as_float((a19 << 4) | 0x3f800000u) * 6.2831855f);
                     float shape = pc.d + np, boost = 1.0f;
                     if (shape < 1.0f) {
-                        boost = ex2_approx(lg2_approx(u01_open(wg.w)) / shape);
+                        const uint32_t b17 = ((w.z & 0xffu) << 9) | (w.w & 0x1ffu);
+                        const float ub = __uint_as_float((b17 << 6) | 0x3f800020u) - 1.0f;         // (k + 0.5) 2^-17
+                        boost = ex2_approx(lg2_approx(ub) / shape);
                         shape += 1.0f;
                     }
                     const float md = shape - (1.0f / 3.0f);
                     const float mc = rsqrt_approx(9.0f * md);
                     float gam;
-                    if (mt_trial(x, u01_open(wg.z), md, mc, gam)) {
+                    if (mt_trial(x, u01_open(w.w), md, mc, gam)) {
                         const float Vn = __fmul_rn(pc.f_scale, 2.0f * gam * boost);   // f_scale = c / 2
                         acc = __fadd_rn(acc, Vn);
                         V = Vn;
@@ -547,13 +553,16 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
     cudaError_t err;
     if (p.rng == NMCH_RNG_PHILOX) {
         std::vector<EmPoint> pts(n_points);
-        bool all_fast = true;
         for (int i = 0; i < n_points; ++i) {
             pts[i] = own ? fold_em_point(p, p.k, p.theta, p.sigma) : fold_em_point(p, k[i], theta[i], sigma[i]);
-            all_fast = all_fast && pts[i].fast;
+            pts[i].index = i;
             if (!em_point_finite(pts[i]))
                 return engine_fail(NMCH_ERR_ARG, "EM: parameters out of the representable range (k dt or sigma^2 too small / large)");
         }
+        // group the points by sampler: the split points first, then the Poisson-mixture points (each keeps its index)
+        std::stable_partition(pts.begin(), pts.end(), [](const EmPoint &q) { return q.fast != 0; });
+        int n_fast = 0;
+        for (const EmPoint &q : pts) n_fast += q.fast ? 1 : 0;
         int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(EmPoint));
         if (rc) return rc;
         const EmPoint *d_pts = nullptr;
@@ -579,18 +588,22 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
         L.lnS0_rT = (float)(std::log((double)p.S_0) + (double)p.r * (double)p.T);
         L.pt0 = pts[0];
         ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
-        dim3 grid((unsigned)bpp, (unsigned)n_points, 1);
         cudaFuncAttributes attr{};
-        if (all_fast) {
+        dim3 grid((unsigned)bpp, 1, 1);
+        if (n_fast > 0) {
+            grid.y = (unsigned)n_fast;
             em_native_kernel<false><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
             cudaFuncGetAttributes(&attr, em_native_kernel<false>);
-        } else {
-            em_native_kernel<true><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
-            cudaFuncGetAttributes(&attr, em_native_kernel<true>);
+        }
+        if (n_fast < n_points) {
+            grid.y = (unsigned)(n_points - n_fast);
+            em_native_kernel<true><<<grid, kEmThreads, 0, stream>>>(L, d_pts ? d_pts + n_fast : nullptr, rb, S_out, V_out);
+            if (n_fast == 0) cudaFuncGetAttributes(&attr, em_native_kernel<true>);
+            else e->launches += 1;                           // a grid with both kinds of points is two launches
         }
         err = cudaGetLastError();
         if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_native_kernel", err);
-        e->kinfo = KernelInfo{(int)grid.x, (int)grid.y, kEmThreads, 1, attr.numRegs,
+        e->kinfo = KernelInfo{(int)grid.x, n_points, kEmThreads, 1, attr.numRegs,
                               (int)(sizeof(EmLaunch) + sizeof(const EmPoint *) + sizeof(ReduceBuffers) + 2 * sizeof(float *))};
         e->em_calls += (unsigned long long)n_points;
         return NMCH_OK;
