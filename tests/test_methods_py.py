@@ -44,3 +44,28 @@ def test_python_method_objects_match_engine_and_text_format():
         assert abs(m.get_err() - o.get_err(512 * 16, m.get_strike_price(), m.get_price_squared())) < 1e-9
         m.finalize()
         m.finalize()
+
+
+@pytest.mark.gpu
+def test_python_opt_in_fe_streams_select_the_engine_modes():
+    """dense= (Philox tag) and fast= (XORWOW tag) pick the opt-in FE streams; EM classes ignore them, as in C++."""
+    from nmch_b200 import engine as E
+    from nmch_b200 import methods as M
+    args = (512, 16, 1.0, 1.0, 0.1, 0.0, 0.5, -0.7, 0.1, 0.3, 100)
+    for tag, kw, mode in ((M.PHILOX, dict(dense=True), E.RNG_PHILOX_DENSE), (M.XORWOW, dict(fast=True), E.RNG_XORWOW_FAST)):
+        m = M.NMCH_FE_K3_MM(*args, tag, **kw)
+        m.init(1234)
+        m.compute()
+        with E.Engine(NTPB=512, NB=16, N=100, rng=mode) as e:
+            e.init(1234)
+            want = e.compute()
+        assert m.last_moments.sum_payoff == want.sum_payoff
+        m.finalize()
+    m = M.NMCH_EM_K3_MM(*args, M.XORWOW, fast=True)            # FE-only option: the EM class stays draw-compatible
+    m.init(1234)
+    m.compute()
+    with E.Engine(NTPB=512, NB=16, N=100, method=E.METHOD_EM, rng=E.RNG_XORWOW_COMPAT) as e:
+        e.init(1234)
+        want = e.compute()
+    assert m.last_moments.sum_payoff == want.sum_payoff
+    m.finalize()
