@@ -2,7 +2,7 @@
  * nmch_b200.h -- C ABI of the B200-native Heston Monte-Carlo engine.
  *
  * This is the drop-in boundary between the reference's C++ method API (layer L3:
- * nmch::methods::NMCH_FE_* / NMCH_EM_*, /root/reference/include/NMCH/methods/*.hpp) and the
+ * nmch::methods::NMCH_FE_* / NMCH_EM_*, /root/reference/include/NMCH/methods/NMCH_{FE,EM}.hpp) and the
  * hand-written sm_100a kernels.  Plain pointers and sizes only; no C++/torch types.
  * Every entry point names the reference interface it replaces (paths relative to
  * /root/reference).  The reference-side binding is shown in INTEGRATION.md.
@@ -143,7 +143,7 @@ int nmch_engine_launch_info(const nmch_engine_t *e, nmch_launch_info_t *out);
  * device g with disjoint generator subsequences (global path index = subsequence, random.cu:8-9), and ONE
  * ncclAllReduce(ncclDouble, ncclSum) over NVLink of the 2*n_points partial moments per compute()/explore().
  * The reference has no multi-GPU path ("Distributed backend: none"); a group of 1 is a plain
- * engine and needs no NCCL.  The C++ method classes (include/NMCH/methods/*.hpp) sit on this API. */
+ * engine and needs no NCCL.  The C++ method classes (include/NMCH/methods/ headers) sit on this API. */
 typedef struct nmch_group nmch_group_t;
 int nmch_group_create(const nmch_params_t *params, int n_gpus, nmch_group_t **out);
 int nmch_group_init(nmch_group_t *g, unsigned long long seed);
