@@ -129,8 +129,9 @@ def cpu_baseline(method: str, N: int, budget_s: float = 12.0):
                                       f"{n_big} paths x {N} steps, {dt:.2f} s, {threads} OpenMP threads"}
 
 
-def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3):
-    """The reference's own CUDA build (unmodified sources, nvcc -arch=sm_100) on this GPU, if shipped."""
+def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3, with_ours: bool = True):
+    """The reference's own CUDA build (unmodified sources, nvcc -arch=sm_100) on this GPU, if shipped.
+    with_ours=False (the reference arm): only the reference binary runs -- nothing of this engine is loaded."""
     exe = os.path.join(ROOT, "oracle", "_ref", "nmch_ref_harness")
     if not os.path.exists(exe):
         return None
@@ -152,6 +153,8 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3):
             units = n * N if method == "fe" else n
             out[rng] = {"value": units / (ms * 1e-3), "exec_ms": ms, "init_ms": rows[0]["init_ms"],
                         "E": rows[-1]["E"], "E2": rows[-1]["E2"]}
+            if not with_ours:
+                continue
             # same seed, same calls through OUR draw-compatible stream mode: identical results, our timing
             try:
                 from nmch_b200 import engine as E
@@ -184,10 +187,11 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3):
         except Exception as ex:  # noqa: BLE001
             out[rng] = {"error": str(ex)[:200]}
     out["what"] = (f"reference NMCH_{method.upper()}_K3_MM<rng> (unmodified sources, -O3 -arch=sm_100), 512 x {n // 512} "
-                   f"paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); unit as `unit`; ours_same_draws = "
-                   "this engine in the draw-compatible mode for that tag, same seed and calls (relative difference of E[X]); "
-                   "ours_same_stream_fast = the same XORWOW integer draws through the native fast-math step "
-                   "(NMCH_RNG_XORWOW_FAST)")
+                   f"paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); unit as `unit`")
+    if with_ours:
+        out["what"] += ("; ours_same_draws = this engine in the draw-compatible mode for that tag, same seed and calls "
+                        "(relative difference of E[X]); ours_same_stream_fast = the same XORWOW integer draws through "
+                        "the native fast-math step (NMCH_RNG_XORWOW_FAST)")
     return out
 
 
@@ -249,7 +253,7 @@ def main():
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "edo01/NMCH is CUDA-only; its hot loop restated in C (oracle/) is what runs on the host cores"}
         if not args.no_reference_cuda:
-            line["reference_cuda"] = reference_cuda(args.method, log2_paths, N)
+            line["reference_cuda"] = reference_cuda(args.method, log2_paths, N, with_ours=False)
         print(json.dumps(line))
         return 0
 
