@@ -9,8 +9,10 @@
 //   d > 1/2 :  Gamma(d + Poisson(l)) =d= (Z + sqrt(2 l))^2 / 2 + Gamma(d - 1/2)           (one normal, one gamma
 //              of CONSTANT shape: Marsaglia-Tsang constants are per-point, no Poisson, no data-dependent regime)
 //   d <= 1/2:  Poisson (inversion below 10, Hoermann PTRS above) then Marsaglia-Tsang gamma of shape d + N
-//   Rejections do not loop inside a step: every loop iteration is ONE trial on a fresh Philox block and a lane
-//   commits its step only if the trial accepted, so a warp never waits on its slowest lane's retry.
+//   Rejections do not loop inside a step: every loop iteration is a trial on fresh Philox bits (split: four trials
+//   per three blocks; mixture: a Poisson and a gamma trial from disjoint bits of one block) and a lane commits its
+//   step only if the trial accepted, so a warp never waits on its slowest lane's retry.  One instantiation per
+//   sampler; a grid holding both kinds of points is launched as two kernels over its points grouped by kind.
 // em_compat_kernel -- validation path: the reference's own draw sequence (cuRAND's curand_poisson /
 //   curand_normal / curand_uniform on a cuRAND-layout state) and its FP32 expressions, so results can be
 //   compared with the reference's CUDA build on identical seeds.
