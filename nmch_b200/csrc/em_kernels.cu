@@ -155,6 +155,26 @@ __device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t
     return (v1 > 0.0f) && (lg2_approx(u01_open(wc)) < rhs);
 }
 
+// The same trial for points whose gamma shape needs no boost (d >= 3/2): three fields suffice, and they fit in TWO
+// words -- wa: top 23 bits -> radius uniform, wc: top 23 bits -> accept-test uniform, angle = wa[8:0] : wc[8:0]
+// (18 bits; an equispaced grid of 2^18 angles keeps every trigonometric moment below that order exact) -- so a Philox
+// block serves two trials.
+__device__ __forceinline__ bool em_fast_trial_packed(uint32_t wa, uint32_t wc, const EmPoint &pc, float &zp, float &g2)
+{
+    const float rad = sqrt_approx(-lg2_approx(u01_open(wa)));
+    const uint32_t am = ((wa & 0x1ffu) << 14) | ((wc & 0x1ffu) << 5);
+    const float ang = __uint_as_float(am | 0x3f800000u) * 6.2831855f;
+    zp = rad * sin_approx(ang);
+    const float xp = rad * cos_approx(ang);
+    const float v1 = fmaf(pc.f_c, xp, 1.0f);
+    const float v = v1 * v1 * v1;
+    const float x2 = xp * xp;
+    float rhs = fmaf(x2, pc.f_h, fmaf(-pc.f_dl, v, pc.f_dl));
+    rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
+    g2 = pc.f_g2s * v;
+    return (v1 > 0.0f) && (lg2_approx(u01_open(wc)) < rhs);
+}
+
 // Block shape of the native kernel (tuning builds may override: -DNMCHB_EM_THREADS=.. -DNMCHB_EM_MINB=..)
 #ifndef NMCHB_EM_THREADS
 #define NMCHB_EM_THREADS 256
@@ -164,10 +184,14 @@ __device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t
 #endif
 constexpr int kEmThreads = NMCHB_EM_THREADS;
 
-// SLOW = false: the chi-square split (points with d > 1/2); SLOW = true: the Poisson mixture (d <= 1/2).  A sweep whose
-// grid holds both kinds is two launches, each over its own points (pts[] is grouped by kind on the host and carries the
-// caller's index): one loop per kernel keeps both free of spills, and no block pays for the other kind's code.
-template <bool SLOW>
+// KIND: kEmSplit = the chi-square split (points with d > 1/2, four trials per three Philox blocks, boost uniform
+// available); kEmSplitPacked = the split for points that need no boost (d >= 3/2, two trials per block);
+// kEmMixture = the Poisson mixture (d <= 1/2).  A sweep whose grid holds several kinds is one launch per kind, each over
+// its own points (pts[] is grouped by kind on the host and carries the caller's index): one loop per kernel keeps all
+// of them free of spills, and no block pays for another kind's code.
+constexpr int kEmSplit = 0, kEmMixture = 1, kEmSplitPacked = 2;
+
+template <int KIND>
 __global__ void __launch_bounds__(kEmThreads, NMCHB_EM_MINB)
 em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__ pts, ReduceBuffers rb,
                  float *__restrict__ S_out, float *__restrict__ V_out)
@@ -194,7 +218,26 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         };
         uint32_t blk = 0;
         int step = valid ? 0 : L.N;                          // lanes past the end of the shard take part in the votes only
-        if constexpr (!SLOW) {
+        if constexpr (KIND == kEmSplitPacked) {
+            // chi-square split, no boost: two trials per Philox block, four per iteration (em_fast_trial_packed)
+            while (__any_sync(0xffffffffu, step < L.N)) {
+                const U4 b0 = next_block(blk), b1 = next_block(blk + 1u);
+                blk += 2u;
+                const uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float zp, g2;
+                    const bool ok = em_fast_trial_packed(w[2 * j], w[2 * j + 1], pc, zp, g2);
+                    const float t = fmaf(pc.f_t1, zp, sqrt_approx(pc.f_ev * V));
+                    const float Vn = fmaf(t, t, g2);
+                    if (ok && step < L.N) {
+                        acc = __fadd_rn(acc, Vn);
+                        V = Vn;
+                        ++step;
+                    }
+                }
+            }
+        } else if constexpr (KIND == kEmSplit) {
             // chi-square split.  A trial needs four 23-bit fields (radius, angle, accept-test uniform, shape<1 boost
             // uniform) = 92 bits, so FOUR trials share THREE Philox blocks: trial j takes words 3j..3j+2 (em_fast_trial).
             // The generator multiplies are the scarce resource, a quarter of them is saved.
@@ -561,10 +604,12 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
             if (!em_point_finite(pts[i]))
                 return engine_fail(NMCH_ERR_ARG, "EM: parameters out of the representable range (k dt or sigma^2 too small / large)");
         }
-        // group the points by sampler: the split points first, then the Poisson-mixture points (each keeps its index)
-        std::stable_partition(pts.begin(), pts.end(), [](const EmPoint &q) { return q.fast != 0; });
-        int n_fast = 0;
-        for (const EmPoint &q : pts) n_fast += q.fast ? 1 : 0;
+        // group the points by sampler (each keeps its index): split with boost, split without boost, Poisson mixture
+        auto kind_of = [](const EmPoint &q) { return !q.fast ? kEmMixture : (q.inv_a != 0.0f ? kEmSplit : kEmSplitPacked); };
+        auto rank_of = [&](const EmPoint &q) { const int kd = kind_of(q); return kd == kEmSplit ? 0 : (kd == kEmSplitPacked ? 1 : 2); };
+        std::stable_sort(pts.begin(), pts.end(), [&](const EmPoint &a, const EmPoint &b) { return rank_of(a) < rank_of(b); });
+        int n_kind[3] = {0, 0, 0};                            // in launch order: split, split packed, mixture
+        for (const EmPoint &q : pts) n_kind[rank_of(q)] += 1;
         int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(EmPoint));
         if (rc) return rc;
         const EmPoint *d_pts = nullptr;
@@ -592,17 +637,25 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
         ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
         cudaFuncAttributes attr{};
         dim3 grid((unsigned)bpp, 1, 1);
-        if (n_fast > 0) {
-            grid.y = (unsigned)n_fast;
-            em_native_kernel<false><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
-            cudaFuncGetAttributes(&attr, em_native_kernel<false>);
+        int first = 0, launched = 0;
+        for (int r = 0; r < 3; ++r) {
+            if (n_kind[r] == 0) continue;
+            grid.y = (unsigned)n_kind[r];
+            const EmPoint *sub = d_pts ? d_pts + first : nullptr;
+            if (r == 0) {
+                em_native_kernel<kEmSplit><<<grid, kEmThreads, 0, stream>>>(L, sub, rb, S_out, V_out);
+                if (!launched) cudaFuncGetAttributes(&attr, em_native_kernel<kEmSplit>);
+            } else if (r == 1) {
+                em_native_kernel<kEmSplitPacked><<<grid, kEmThreads, 0, stream>>>(L, sub, rb, S_out, V_out);
+                if (!launched) cudaFuncGetAttributes(&attr, em_native_kernel<kEmSplitPacked>);
+            } else {
+                em_native_kernel<kEmMixture><<<grid, kEmThreads, 0, stream>>>(L, sub, rb, S_out, V_out);
+                if (!launched) cudaFuncGetAttributes(&attr, em_native_kernel<kEmMixture>);
+            }
+            first += n_kind[r];
+            launched += 1;
         }
-        if (n_fast < n_points) {
-            grid.y = (unsigned)(n_points - n_fast);
-            em_native_kernel<true><<<grid, kEmThreads, 0, stream>>>(L, d_pts ? d_pts + n_fast : nullptr, rb, S_out, V_out);
-            if (n_fast == 0) cudaFuncGetAttributes(&attr, em_native_kernel<true>);
-            else e->launches += 1;                           // a grid with both kinds of points is two launches
-        }
+        e->launches += (unsigned long long)(launched - 1);   // a grid with several kinds of points is one launch per kind
         err = cudaGetLastError();
         if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_native_kernel", err);
         e->kinfo = KernelInfo{(int)grid.x, n_points, kEmThreads, 1, attr.numRegs,
