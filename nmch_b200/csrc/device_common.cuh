@@ -1,8 +1,19 @@
 // device_common.cuh -- Philox4x32-10, approximate-math wrappers and the FP64 payoff reduction
 // shared by the FE and EM kernels (sm_100a).
 #pragma once
+#include <cassert>
 #include <cstdint>
 #include <cuda_runtime.h>
+
+// Checked build (-DNMCHB_CHECKS, nmch_b200/_build.py build_checked()): device-side asserts on every index the kernels
+// form (path, tile, point, partial and ticket slots, state arrays).  A failed assert traps the kernel and the next
+// CUDA call of the engine returns NMCH_ERR_CUDA.  Stands in for compute-sanitizer, which is closed on the B200 pool;
+// tests/test_gpu_checked_build.py runs the ragged / 64-bit-index / shard / multi-tile cases through that library.
+#ifdef NMCHB_CHECKS
+#define NMCHB_ASSERT(cond) assert(cond)
+#else
+#define NMCHB_ASSERT(cond) ((void)0)
+#endif
 
 namespace nmchb {
 
@@ -158,6 +169,25 @@ __device__ __forceinline__ float bits_to_1_2(uint32_t x)
     return __uint_as_float((x >> 9) | 0x3f800000u);
 }
 
+// Payoff (S_T - K)^+ of one path as the FP64 summand.  fmaxf returns its non-NaN operand, so a path that went NaN
+// (a sampler's hang guard, parameters at the edge of the representable range) would silently count as zero payoff:
+// carry the NaN into the sums instead, where the caller sees it.
+__device__ __forceinline__ double payoff_or_nan(float S, float K)
+{
+    const float pay = fmaxf(0.0f, S - K);
+    return (S == S) ? (double)pay : (double)S;
+}
+
+// (x & mask) | bits as ONE LOP3: written as x & mask | bits with two literals, ptxas emits two LOP3 (one immediate per
+// instruction); with the mask in a register (a uniform register after hoisting) it is a single one.  ALU-pipe
+// instructions cost two issue cycles each on this part (profiles/r02_pipe_rates2.txt), so this is worth an asm.
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t bits)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(mask), "r"(bits));
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // Payoff moments: per-thread FP64 pair -> warp shuffle -> shared memory -> one FP64 partial per
 // block -> the last block of the point (atomic ticket) folds the partials in index order with
@@ -206,6 +236,7 @@ __device__ __forceinline__ void block_reduce_and_finish(double a, double b, doub
         a = warp_sum(a);
         b = warp_sum(b);
         if (lane == 0) {
+            NMCHB_ASSERT(point >= 0 && block_in_point >= 0 && block_in_point < blocks_per_point);
             partials[(size_t)point * blocks_per_point + block_in_point] = make_double2(a, b);
             __threadfence();
             const unsigned int t = atomicAdd(&tickets[point], 1u);

@@ -8,11 +8,15 @@
 // em_native_kernel -- the product path.  V'/c is a scaled noncentral chi-square, sampled exactly by
 //   d > 1/2 :  Gamma(d + Poisson(l)) =d= (Z + sqrt(2 l))^2 / 2 + Gamma(d - 1/2)           (one normal, one gamma
 //              of CONSTANT shape: Marsaglia-Tsang constants are per-point, no Poisson, no data-dependent regime)
+//              A trial takes 64 bits (23-bit radius, 18-bit angle, 23-bit accept uniform): two trials per Philox block.
+//              Shape d - 1/2 < 1 needs the boost Gamma(a) = Gamma(a+1) U^(1/a); its uniform costs no random bits:
+//              the accept test  -lg2 u < t  leaves, on acceptance, the excess  -lg2 u - t  as a fresh exponential
+//              (memorylessness), so U = 2^-(excess) is uniform and independent of the accepted proposal.
 //   d <= 1/2:  Poisson (inversion below 10, Hoermann PTRS above) then Marsaglia-Tsang gamma of shape d + N
-//   Rejections do not loop inside a step: every loop iteration is a trial on fresh Philox bits (split: four trials
-//   per three blocks; mixture: a Poisson and a gamma trial from disjoint bits of one block) and a lane commits its
-//   step only if the trial accepted, so a warp never waits on its slowest lane's retry.  One instantiation per
-//   sampler; a grid holding both kinds of points is launched as two kernels over its points grouped by kind.
+//   Rejections do not loop inside a step: every loop iteration is a group of trials on fresh Philox bits and a lane
+//   commits its step only if the trial accepted, so a warp never waits on its slowest lane's retry.  One
+//   instantiation per sampler for launches whose points are all of one kind; a grid holding several kinds is ONE
+//   launch of the kEmAny instantiation, which picks the sampler per block from the point record (block-uniform).
 // em_compat_kernel -- validation path: the reference's own draw sequence (cuRAND's curand_poisson /
 //   curand_normal / curand_uniform on a cuRAND-layout state) and its FP32 expressions, so results can be
 //   compared with the reference's CUDA build on identical seeds.
@@ -45,7 +49,7 @@ struct EmPoint {
     float f_ev;         // lc * c = e^{-k dt}
     float f_scale;      // c / 2                   (Poisson-mixture path)
     float k, ktheta_T, inv_sigma;
-    int   fast;         // 1: d - 1/2 > 0, chi-square split; 0: Poisson-mixture path
+    int   kind;         // kEmSplit (boosted gamma, 1/2 < d < 3/2), kEmSplitPacked (d >= 3/2) or kEmMixture (d <= 1/2)
     int   index;        // position of the point in the caller's list (stream id, result slot): launches group points by kind
 };
 
@@ -128,51 +132,33 @@ __device__ __forceinline__ float poisson_inversion(float mu, float u)
     return k;
 }
 
-// One trial of the chi-square split from three Philox words, every constant folded on the host, no data-dependent
+// One trial of the chi-square split from TWO Philox words, every constant folded on the host, no data-dependent
 // branch:   2 V'/c = (Z + sqrt(2 l))^2 + 2 Gamma(a),   Z = c0 z', X = c0 x' from one Box-Muller pair.
-//   wa: top 23 bits -> radius uniform      wb: top 23 bits -> angle      wc: top 23 bits -> accept-test uniform
-//   the shape<1 boost uniform is spliced from the bits those mantissas leave over: wa[8:0] : wb[8:0] : wc[4:0]
-// Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp: accept iff v1 > 0 and
-//   log2 u < (x^2/2 + d (1 - v)) log2 e + d log2 v          (the exact test; no squeeze, hence no divergence)
+//   radius uniform = wa[31:9] (23 bits)    angle = wa[8:0] : wc[31:23] (18 bits; an equispaced grid of 2^18 angles keeps
+//   every trigonometric moment below that order exact)    accept-test uniform = wc[22:0] (23 bits)
+// Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp, v = (1 + c x)^3: accept iff v > 0 and
+//   lg2 u < rhs = (x^2/2 + d (1 - v)) log2 e + d log2 v         (the exact test; no squeeze, hence no divergence)
+// BOOST (shape a < 1): Gamma(a) = Gamma(a+1) U^(1/a) with U = 2^(lg2 u - rhs): given acceptance, rhs - lg2 u is an
+// exponential (rate ln 2) independent of the proposal -- the accept uniform's unused excess, so no extra random field
+// and one MUFU.EX2 instead of LG2 + EX2.  (Marsaglia-Tsang's acceptance ratio never exceeds one, i.e. rhs <= 0.)
 // Returns accept; zp = Z / c0, g2 = c Gamma(a) (the gamma term already scaled to V').
-__device__ __forceinline__ bool em_fast_trial(uint32_t wa, uint32_t wb, uint32_t wc, const EmPoint &pc, float &zp, float &g2)
+template <bool BOOST>
+__device__ __forceinline__ bool em_split_trial(uint32_t wa, uint32_t wc, const EmPoint &pc, float &zp, float &g2)
 {
     const float rad = sqrt_approx(-lg2_approx(u01_open(wa)));
-    const float ang = bits_to_1_2(wb) * 6.2831855f;
+    // (wa << 14 | wc >> 18) masked to mantissa bits 22..5, exponent of [1, 2) -- one funnel shift, one LOP3
+    const float ang = __uint_as_float(and_or(__funnelshift_r(wc, wa, 18), 0x7fffe0u, 0x3f800000u)) * 6.2831855f;
     zp = rad * sin_approx(ang);
     const float xp = rad * cos_approx(ang);
     const float v1 = fmaf(pc.f_c, xp, 1.0f);
     const float v = v1 * v1 * v1;
     const float x2 = xp * xp;
     float rhs = fmaf(x2, pc.f_h, fmaf(-pc.f_dl, v, pc.f_dl));
-    rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
+    rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);                  // v1 <= 0: lg2 gives NaN (v < 0) or -inf (v = 0), so the
+    const float lu = lg2_approx(__uint_as_float(and_or(wc, 0x7fffffu, 0x3f800000u)) - 0.99999994f);
     g2 = pc.f_g2s * v;
-    if (pc.inv_a != 0.0f) {                                      // shape < 1 boost: Gamma(a) = Gamma(a+1) U^(1/a)
-        const uint32_t m = ((wa & 0x1ffu) << 14) | ((wb & 0x1ffu) << 5) | (wc & 0x1fu);
-        const float ub = __uint_as_float(m | 0x3f800000u) - 0.99999994f;
-        g2 *= ex2_approx(pc.inv_a * lg2_approx(ub));
-    }
-    return (v1 > 0.0f) && (lg2_approx(u01_open(wc)) < rhs);
-}
-
-// The same trial for points whose gamma shape needs no boost (d >= 3/2): three fields suffice, and they fit in TWO
-// words -- wa: top 23 bits -> radius uniform, wc: top 23 bits -> accept-test uniform, angle = wa[8:0] : wc[8:0]
-// (18 bits; an equispaced grid of 2^18 angles keeps every trigonometric moment below that order exact) -- so a Philox
-// block serves two trials.
-__device__ __forceinline__ bool em_fast_trial_packed(uint32_t wa, uint32_t wc, const EmPoint &pc, float &zp, float &g2)
-{
-    const float rad = sqrt_approx(-lg2_approx(u01_open(wa)));
-    const uint32_t am = ((wa & 0x1ffu) << 14) | ((wc & 0x1ffu) << 5);
-    const float ang = __uint_as_float(am | 0x3f800000u) * 6.2831855f;
-    zp = rad * sin_approx(ang);
-    const float xp = rad * cos_approx(ang);
-    const float v1 = fmaf(pc.f_c, xp, 1.0f);
-    const float v = v1 * v1 * v1;
-    const float x2 = xp * xp;
-    float rhs = fmaf(x2, pc.f_h, fmaf(-pc.f_dl, v, pc.f_dl));
-    rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);
-    g2 = pc.f_g2s * v;
-    return (v1 > 0.0f) && (lg2_approx(u01_open(wc)) < rhs);
+    if constexpr (BOOST) g2 *= ex2_approx(pc.inv_a * (lu - rhs));
+    return lu < rhs;                                          // comparison below is false: no separate v1 > 0 test
 }
 
 // Block shape of the native kernel (tuning builds may override: -DNMCHB_EM_THREADS=.. -DNMCHB_EM_MINB=..)
@@ -184,12 +170,87 @@ __device__ __forceinline__ bool em_fast_trial_packed(uint32_t wa, uint32_t wc, c
 #endif
 constexpr int kEmThreads = NMCHB_EM_THREADS;
 
-// KIND: kEmSplit = the chi-square split (points with d > 1/2, four trials per three Philox blocks, boost uniform
-// available); kEmSplitPacked = the split for points that need no boost (d >= 3/2, two trials per block);
-// kEmMixture = the Poisson mixture (d <= 1/2).  A sweep whose grid holds several kinds is one launch per kind, each over
-// its own points (pts[] is grouped by kind on the host and carries the caller's index): one loop per kernel keeps all
-// of them free of spills, and no block pays for another kind's code.
-constexpr int kEmSplit = 0, kEmMixture = 1, kEmSplitPacked = 2;
+// KIND: kEmSplit = the chi-square split with the boosted gamma (1/2 < d < 3/2); kEmSplitPacked = the split for points
+// that need no boost (d >= 3/2); kEmMixture = the Poisson mixture (d <= 1/2); kEmAny = the sampler is read from the
+// point record per block (block-uniform switch) -- what a sweep over points of several kinds launches, ONCE.
+constexpr int kEmSplit = 0, kEmMixture = 1, kEmSplitPacked = 2, kEmAny = 3;
+
+// The variance path of one thread: N exact CIR transitions on Philox blocks 0, 1, ... of its stream.  Returns with
+// V = V_N, acc = V_1 + ... + V_N and blk = the first unused block (the terminal draw takes it).
+template <int KIND, typename NextBlock>
+__device__ __forceinline__ void em_variance_path(const EmLaunch &L, const EmPoint &pc, bool valid, NextBlock next_block,
+                                                 float &V, float &acc, uint32_t &blk)
+{
+    int step = valid ? 0 : L.N;                              // lanes past the end of the shard take part in the votes only
+    if constexpr (KIND == kEmSplit || KIND == kEmSplitPacked) {
+        // chi-square split: two trials per Philox block, four per iteration (em_split_trial).  Only the last FFMA pair
+        // of a trial depends on V, so the four trials of a group overlap.  The loop is warp-uniform (vote): the block
+        // counter is the same in every lane, and with it the path-independent multiplies of a block.
+        while (__any_sync(0xffffffffu, step < L.N)) {
+            const U4 b0 = next_block(blk), b1 = next_block(blk + 1u);
+            blk += 2u;
+            const uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float zp, g2;
+                const bool ok = em_split_trial<KIND == kEmSplit>(w[2 * j], w[2 * j + 1], pc, zp, g2);
+                const float t = fmaf(pc.f_t1, zp, sqrt_approx(pc.f_ev * V));
+                const float Vn = fmaf(t, t, g2);             // = (c/2) ((Z + sqrt(2 l))^2 + 2 Gamma(a))
+                if (ok && step < L.N) {
+                    acc = __fadd_rn(acc, Vn);
+                    V = Vn;
+                    ++step;
+                }
+            }
+        }
+    } else {
+        // Poisson mixture (d <= 1/2): per iteration ONE Philox block feeds a Poisson trial (two 23-bit uniforms)
+        // and, from disjoint bits of the same block, one Marsaglia-Tsang trial for Gamma(d + N) (23-bit radius,
+        // 19-bit angle, 23-bit accept uniform, 17-bit boost uniform: 128 bits in all).  A lane that already holds
+        // N skips the Poisson part, so a gamma retry never re-draws (and never biases) N.
+        // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive),
+        // so the loop terminates; the cap is a belt against a hang: a path that exhausts it ends early with V = NaN,
+        // which the payoff stage below carries into the sums (a NaN result, not a silently dropped path).
+        bool have_np = false;
+        float np = 0.0f;
+        const uint32_t max_blocks = 64u * (uint32_t)L.N + 4096u;
+        while (step < L.N) {
+            if (blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
+            const U4 w = next_block(blk++);
+            if (!have_np) {
+                const float mu = pc.lc * V;
+                if (mu < 10.0f) {
+                    np = poisson_inversion(mu, u01_open(w.x));
+                    have_np = true;
+                } else {
+                    have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), np);
+                }
+            }
+            if (have_np) {
+                const uint32_t a19 = ((w.x & 0x1ffu) << 10) | ((w.y & 0x1ffu) << 1) | ((w.z >> 8) & 1u);
+                const float rad = sqrt_approx(-1.38629436f * lg2_approx(u01_open(w.z)));      // sqrt(-2 ln u)
+                const float x = rad * sin_approx(__uint_as_float((a19 << 4) | 0x3f800000u) * 6.2831855f);
+                float shape = pc.d + np, boost = 1.0f;
+                if (shape < 1.0f) {
+                    const uint32_t b17 = ((w.z & 0xffu) << 9) | (w.w & 0x1ffu);
+                    const float ub = __uint_as_float((b17 << 6) | 0x3f800020u) - 1.0f;         // (k + 0.5) 2^-17
+                    boost = ex2_approx(lg2_approx(ub) / shape);
+                    shape += 1.0f;
+                }
+                const float md = shape - (1.0f / 3.0f);
+                const float mc = rsqrt_approx(9.0f * md);
+                float gam;
+                if (mt_trial(x, u01_open(w.w), md, mc, gam)) {
+                    const float Vn = __fmul_rn(pc.f_scale, 2.0f * gam * boost);   // f_scale = c / 2
+                    acc = __fadd_rn(acc, Vn);
+                    V = Vn;
+                    ++step;
+                    have_np = false;
+                }
+            }
+        }
+    }
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(kEmThreads, NMCHB_EM_MINB)
@@ -200,6 +261,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
     const int point = pc.index;
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
+    NMCHB_ASSERT(point >= 0 && point < L.n_points);
     // first_path is a multiple of 4096 (checked at create): the high counter word is the same for the whole
     // block, so the multiplies of a Philox block that do not depend on the path stay on the uniform datapath
     const unsigned long long g0 = L.first_path + (unsigned long long)blockIdx.x * blockDim.x;
@@ -217,95 +279,12 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
             return philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv, L.keys);
         };
         uint32_t blk = 0;
-        int step = valid ? 0 : L.N;                          // lanes past the end of the shard take part in the votes only
-        if constexpr (KIND == kEmSplitPacked) {
-            // chi-square split, no boost: two trials per Philox block, four per iteration (em_fast_trial_packed)
-            while (__any_sync(0xffffffffu, step < L.N)) {
-                const U4 b0 = next_block(blk), b1 = next_block(blk + 1u);
-                blk += 2u;
-                const uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float zp, g2;
-                    const bool ok = em_fast_trial_packed(w[2 * j], w[2 * j + 1], pc, zp, g2);
-                    const float t = fmaf(pc.f_t1, zp, sqrt_approx(pc.f_ev * V));
-                    const float Vn = fmaf(t, t, g2);
-                    if (ok && step < L.N) {
-                        acc = __fadd_rn(acc, Vn);
-                        V = Vn;
-                        ++step;
-                    }
-                }
-            }
-        } else if constexpr (KIND == kEmSplit) {
-            // chi-square split.  A trial needs four 23-bit fields (radius, angle, accept-test uniform, shape<1 boost
-            // uniform) = 92 bits, so FOUR trials share THREE Philox blocks: trial j takes words 3j..3j+2 (em_fast_trial).
-            // The generator multiplies are the scarce resource, a quarter of them is saved.
-            // Only the last FFMA pair of a trial depends on V, so the four trials of a group overlap.
-            // The loop is warp-uniform (vote): the block counter is the same in every lane.
-            while (__any_sync(0xffffffffu, step < L.N)) {
-                const U4 b0 = next_block(blk), b1 = next_block(blk + 1u), b2 = next_block(blk + 2u);
-                blk += 3u;
-                const uint32_t w[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float zp, g2;
-                    const bool ok = em_fast_trial(w[3 * j], w[3 * j + 1], w[3 * j + 2], pc, zp, g2);
-                    const float t = fmaf(pc.f_t1, zp, sqrt_approx(pc.f_ev * V));
-                    const float Vn = fmaf(t, t, g2);            // = (c/2) ((Z + sqrt(2 l))^2 + 2 Gamma(a))
-                    if (ok && step < L.N) {
-                        acc = __fadd_rn(acc, Vn);
-                        V = Vn;
-                        ++step;
-                    }
-                }
-            }
+        if constexpr (KIND == kEmAny) {
+            if (pc.kind == kEmSplitPacked) em_variance_path<kEmSplitPacked>(L, pc, valid, next_block, V, acc, blk);
+            else if (pc.kind == kEmSplit) em_variance_path<kEmSplit>(L, pc, valid, next_block, V, acc, blk);
+            else em_variance_path<kEmMixture>(L, pc, valid, next_block, V, acc, blk);
         } else {
-            // Poisson mixture (d <= 1/2): per iteration ONE Philox block feeds a Poisson trial (two 23-bit uniforms)
-            // and, from disjoint bits of the same block, one Marsaglia-Tsang trial for Gamma(d + N) (23-bit radius,
-            // 19-bit angle, 23-bit accept uniform, 17-bit boost uniform: 128 bits in all).  A lane that already holds
-            // N skips the Poisson part, so a gamma retry never re-draws (and never biases) N.
-            // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive),
-            // so the loop terminates; the cap is a belt against a hang: a path that exhausts it ends early and poisons
-            // the sum with NaN instead of stalling the GPU.  (The split path is not taxed with it.)
-            bool have_np = false;
-            float np = 0.0f;
-            const uint32_t max_blocks = 64u * (uint32_t)L.N + 4096u;
-            while (step < L.N) {
-                if (blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
-                const U4 w = next_block(blk++);
-                if (!have_np) {
-                    const float mu = pc.lc * V;
-                    if (mu < 10.0f) {
-                        np = poisson_inversion(mu, u01_open(w.x));
-                        have_np = true;
-                    } else {
-                        have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), np);
-                    }
-                }
-                if (have_np) {
-                    const uint32_t a19 = ((w.x & 0x1ffu) << 10) | ((w.y & 0x1ffu) << 1) | ((w.z >> 8) & 1u);
-                    const float rad = sqrt_approx(-1.38629436f * lg2_approx(u01_open(w.z)));      // sqrt(-2 ln u)
-                    const float x = rad * sin_approx(__uint_as_float((a19 << 4) | 0x3f800000u) * 6.2831855f);
-                    float shape = pc.d + np, boost = 1.0f;
-                    if (shape < 1.0f) {
-                        const uint32_t b17 = ((w.z & 0xffu) << 9) | (w.w & 0x1ffu);
-                        const float ub = __uint_as_float((b17 << 6) | 0x3f800020u) - 1.0f;         // (k + 0.5) 2^-17
-                        boost = ex2_approx(lg2_approx(ub) / shape);
-                        shape += 1.0f;
-                    }
-                    const float md = shape - (1.0f / 3.0f);
-                    const float mc = rsqrt_approx(9.0f * md);
-                    float gam;
-                    if (mt_trial(x, u01_open(w.w), md, mc, gam)) {
-                        const float Vn = __fmul_rn(pc.f_scale, 2.0f * gam * boost);   // f_scale = c / 2
-                        acc = __fadd_rn(acc, Vn);
-                        V = Vn;
-                        ++step;
-                        have_np = false;
-                    }
-                }
-            }
+            em_variance_path<KIND>(L, pc, valid, next_block, V, acc, blk);
         }
         // terminal draw (NMCH_EM.cu:247-260, generalised to S_0, r, T)
         const U4 w = next_block(blk);
@@ -319,7 +298,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
     }
     double pay = 0.0;
     if (valid) {
-        pay = (double)fmaxf(0.0f, S - L.K);
+        pay = payoff_or_nan(S, L.K);
         if (S_out != nullptr && point == L.n_points - 1) {
             S_out[idx] = S;
             V_out[idx] = V;
@@ -550,7 +529,8 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
     pt.k = kf;
     pt.ktheta_T = (float)(k * theta * (double)p.T);
     pt.inv_sigma = (float)(1.0 / sigma);
-    pt.fast = (pt.a > 1e-3f) ? 1 : 0;      // tiny or negative d - 1/2 goes through the Poisson mixture
+    // tiny or negative d - 1/2 goes through the Poisson mixture
+    pt.kind = !(pt.a > 1e-3f) ? kEmMixture : (pt.inv_a != 0.0f ? kEmSplit : kEmSplitPacked);
     return pt;
 }
 
@@ -604,12 +584,11 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
             if (!em_point_finite(pts[i]))
                 return engine_fail(NMCH_ERR_ARG, "EM: parameters out of the representable range (k dt or sigma^2 too small / large)");
         }
-        // group the points by sampler (each keeps its index): split with boost, split without boost, Poisson mixture
-        auto kind_of = [](const EmPoint &q) { return !q.fast ? kEmMixture : (q.inv_a != 0.0f ? kEmSplit : kEmSplitPacked); };
-        auto rank_of = [&](const EmPoint &q) { const int kd = kind_of(q); return kd == kEmSplit ? 0 : (kd == kEmSplitPacked ? 1 : 2); };
+        // group the points by sampler (each keeps its index), slowest sampler first so that the tail of the launch is
+        // made of the cheapest blocks: Poisson mixture, split with boost, split without boost
+        auto rank_of = [](const EmPoint &q) { return q.kind == kEmMixture ? 0 : (q.kind == kEmSplit ? 1 : 2); };
         std::stable_sort(pts.begin(), pts.end(), [&](const EmPoint &a, const EmPoint &b) { return rank_of(a) < rank_of(b); });
-        int n_kind[3] = {0, 0, 0};                            // in launch order: split, split packed, mixture
-        for (const EmPoint &q : pts) n_kind[rank_of(q)] += 1;
+        const bool one_kind = pts.front().kind == pts.back().kind;
         int rc = engine_ensure_buffers(e, n_points, bpp, own ? 0 : (size_t)n_points * sizeof(EmPoint));
         if (rc) return rc;
         const EmPoint *d_pts = nullptr;
@@ -636,26 +615,23 @@ int em_launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const 
         L.pt0 = pts[0];
         ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
         cudaFuncAttributes attr{};
-        dim3 grid((unsigned)bpp, 1, 1);
-        int first = 0, launched = 0;
-        for (int r = 0; r < 3; ++r) {
-            if (n_kind[r] == 0) continue;
-            grid.y = (unsigned)n_kind[r];
-            const EmPoint *sub = d_pts ? d_pts + first : nullptr;
-            if (r == 0) {
-                em_native_kernel<kEmSplit><<<grid, kEmThreads, 0, stream>>>(L, sub, rb, S_out, V_out);
-                if (!launched) cudaFuncGetAttributes(&attr, em_native_kernel<kEmSplit>);
-            } else if (r == 1) {
-                em_native_kernel<kEmSplitPacked><<<grid, kEmThreads, 0, stream>>>(L, sub, rb, S_out, V_out);
-                if (!launched) cudaFuncGetAttributes(&attr, em_native_kernel<kEmSplitPacked>);
-            } else {
-                em_native_kernel<kEmMixture><<<grid, kEmThreads, 0, stream>>>(L, sub, rb, S_out, V_out);
-                if (!launched) cudaFuncGetAttributes(&attr, em_native_kernel<kEmMixture>);
-            }
-            first += n_kind[r];
-            launched += 1;
+        // ONE launch: blockIdx.y = point.  All points of one kind: that sampler's own instantiation; otherwise kEmAny,
+        // whose blocks pick the sampler from their point record.
+        dim3 grid((unsigned)bpp, (unsigned)n_points, 1);
+        const int kind = one_kind ? pts.front().kind : kEmAny;
+        if (kind == kEmSplit) {
+            em_native_kernel<kEmSplit><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            cudaFuncGetAttributes(&attr, em_native_kernel<kEmSplit>);
+        } else if (kind == kEmSplitPacked) {
+            em_native_kernel<kEmSplitPacked><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            cudaFuncGetAttributes(&attr, em_native_kernel<kEmSplitPacked>);
+        } else if (kind == kEmMixture) {
+            em_native_kernel<kEmMixture><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            cudaFuncGetAttributes(&attr, em_native_kernel<kEmMixture>);
+        } else {
+            em_native_kernel<kEmAny><<<grid, kEmThreads, 0, stream>>>(L, d_pts, rb, S_out, V_out);
+            cudaFuncGetAttributes(&attr, em_native_kernel<kEmAny>);
         }
-        e->launches += (unsigned long long)(launched - 1);   // a grid with several kinds of points is one launch per kind
         err = cudaGetLastError();
         if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "em_native_kernel", err);
         e->kinfo = KernelInfo{(int)grid.x, n_points, kEmThreads, 1, attr.numRegs,

@@ -30,12 +30,21 @@ template <int FLOOR, bool PRECISE_V = false>
 __device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, uint32_t wb, float rdt,
                                                float zr, float zc, const FePoint &pc)
 {
+#ifdef NMCHB_FE_I2FP
+    // tuning variant: integer -> float conversion (I2FP) instead of bit splicing; the uniforms are then cuRAND's own
+    // (x * 2^-32 + 2^-33, curand_uniform.h:69-72), 24 bits, in (0, 1]
+    const float u = fmaf(__uint2float_rn(wa), 2.3283064e-10f, 1.1641532e-10f);
+    const float l2 = lg2_approx(u);                   // <= 0
+    const float q = sqrt_approx(-(V * l2));           // sqrt(V) * sqrt(-lg2 u)
+    const float ang = __uint2float_rn(wb) * 1.4629181e-9f;   // 2 pi 2^-32
+#else
     const float f1 = bits_to_1_2(wa);
     const float f2 = bits_to_1_2(wb);
     const float u = f1 - 0.99999994f;                 // (floor(wa/2^9) + 0.5) * 2^-23, in (0,1): exact
     const float l2 = lg2_approx(u);                   // < 0
     const float q = sqrt_approx(-(V * l2));           // sqrt(V) * sqrt(-lg2 u)
     const float ang = f2 * 6.2831855f;                // [2pi, 4pi): same sine/cosine as [0, 2pi)
+#endif
     const float gs = q * sin_approx(ang);
     const float gc = q * cos_approx(ang);
     float m = fmaf(gs, zr, rdt);                      // relative increment; S' = S + S*m keeps r*dt at full precision
@@ -157,7 +166,7 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
         for (int j = 0; j < P; ++j) {
             const unsigned long long idx = local0 + (unsigned long long)(j * THREADS) + threadIdx.x;
             if (idx < L.n_local) {
-                const double pay = (double)fmaxf(0.0f, S[j] - L.K);
+                const double pay = payoff_or_nan(S[j], L.K);
                 acc.x += pay;
                 acc.y += pay * pay;
                 if (S_out != nullptr && point == L.n_points - 1) {
@@ -233,7 +242,9 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
     //   s0 = draw_offset / 2 + point * N = 3 * blk0 + phase0, from the host's pre-divided parts -- a 64-bit division
     //   here would take the block index, and with it the path-independent Philox multiplies, off the uniform datapath
     const unsigned int t0 = L.dense_r0 + (unsigned int)point * L.dense_rN;
-    const unsigned int q0 = (t0 * 43691u) >> 17;      // t0 / 3, exact below 2^17 (t0 <= 2 + 2 * 65534): low multiply + shift only
+    // t0 / 3, exact below 2^17 (t0 <= 2 + 2 * 65534).  The product needs 34 bits: a 32-bit multiply wraps from t0 = 98304
+    // on (a sweep of more than 49151 points with N % 3 == 2), so it is formed in 64 bits (one wide multiply + shift, uniform datapath)
+    const unsigned int q0 = (unsigned int)(((unsigned long long)t0 * 43691ull) >> 17);
     const unsigned long long blk0 = L.dense_q0 + (unsigned long long)point * (unsigned long long)L.dense_qN + (unsigned long long)q0;
     const int phase0 = (int)(t0 - 3u * q0);
 
@@ -307,7 +318,7 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
         for (int j = 0; j < P; ++j) {
             const unsigned long long idx = local0 + (unsigned long long)(j * THREADS) + threadIdx.x;
             if (idx < L.n_local) {
-                const double pay = (double)fmaxf(0.0f, S[j] - L.K);
+                const double pay = payoff_or_nan(S[j], L.K);
                 acc.x += pay;
                 acc.y += pay * pay;
                 if (S_out != nullptr && point == L.n_points - 1) {
@@ -500,7 +511,7 @@ fe_xorwow_fast_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restr
         }
         double pay = 0.0;
         if (valid) {
-            pay = (double)fmaxf(0.0f, S - L.K);
+            pay = payoff_or_nan(S, L.K);
             if (S_out != nullptr && point == L.n_points - 1) {
                 S_out[idx] = S;
                 V_out[idx] = V;

@@ -80,6 +80,10 @@ qe_kernel(const __grid_constant__ QeLaunch L, const QePoint *__restrict__ pts, R
                 Vn = (u <= p) ? 0.0f : __logf((1.0f - p) * rcp_approx(1.0f - u)) * rcp_approx(beta);
                 lnM = __logf(p + beta * (1.0f - p) * rcp_approx(fmaxf(beta - pc.A, 1e-6f)));
             }
+            if (!(m > 0.0f)) {               // theta = 0 and V = 0: the variance is absorbed at zero (psi = 0 * inf above)
+                Vn = 0.0f;
+                lnM = 0.0f;
+            }
             // ln S' = ln S + r dt - ln M - K3 V / 2 + K2 V' + sqrt(K3 V + K4 V') Z_s   (K0* with K1 V folded in)
             const float var = fmaf(pc.K3, V, pc.K4 * Vn);
             lnS += L.r_dt - lnM - 0.5f * pc.K3 * V + pc.K2 * Vn + sqrt_approx(var) * zs;
@@ -89,7 +93,7 @@ qe_kernel(const __grid_constant__ QeLaunch L, const QePoint *__restrict__ pts, R
     double pay = 0.0;
     if (valid) {
         const float S = __expf(lnS);
-        pay = (double)fmaxf(0.0f, S - L.K);
+        pay = payoff_or_nan(S, L.K);
         if (S_out != nullptr && point == L.n_points - 1) {
             S_out[idx] = S;
             V_out[idx] = V;

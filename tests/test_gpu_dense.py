@@ -105,3 +105,25 @@ def test_explore_seek_shards_and_layout_independence():
     np.testing.assert_allclose(S, ref["S"], rtol=2e-3, atol=2e-4)
     with pytest.raises(capi.NmchError):
         E.Engine(NTPB=32, NB=4, N=10, rng=DENSE, method=E.METHOD_EM)
+
+
+def test_explore_beyond_49152_points_with_N_mod_3_equal_2():
+    """the block index of point p is (r0 + p * (N % 3)) / 3; formed with a 32-bit multiply it wrapped from
+    t0 = 98304 on, i.e. for N % 3 == 2 and p >= 49152.  Compare late points of a 60000-point sweep with compute()
+    calls positioned at the same stream offset."""
+    n, N, n_points = 4096, 5, 60000
+    rng = np.random.default_rng(3)
+    k = rng.uniform(0.1, 5.0, n_points).astype(np.float32)
+    th = rng.uniform(0.01, 0.5, n_points).astype(np.float32)
+    sg = rng.uniform(0.1, 1.0, n_points).astype(np.float32)
+    with engine(n, N) as e:
+        e.init(11)
+        ex = e.explore(k, th, sg)
+    for p in (0, 49151, 49152, 49153, 55001, 59999):
+        with engine(n, N) as e:
+            e.init(11)
+            e.seek(2 * N * p)
+            e.set_params(float(k[p]), float(th[p]), float(sg[p]))
+            s = e.compute()
+        assert abs(s.sum_payoff - ex[p].sum_payoff) <= 1e-12 * abs(s.sum_payoff) + 1e-300, p
+        assert abs(s.sum_payoff_sq - ex[p].sum_payoff_sq) <= 1e-12 * abs(s.sum_payoff_sq) + 1e-300, p

@@ -112,6 +112,37 @@ def test_native_matches_analytic_and_martingale():
     assert abs(m.mean - ref["mean"]) < 3 * se
 
 
+@pytest.mark.parametrize("k,theta,sigma,v0", [
+    (0.5, 0.1, 0.3, 0.1),        # d = 1.11: split with the boosted gamma (shape 0.61), the boost recycled from the accept test
+    (0.5, 0.1, 0.42, 0.1),       # d = 0.567: boosted gamma of shape 0.067
+    (0.5, 0.1, 0.32, 0.002),     # d = 0.98 and a small noncentrality: the gamma term dominates
+    (10.0, 0.5, 1.0, 0.1),       # d = 10: split without boost
+    (2.08, 0.108, 0.28, 0.1),    # d = 5.7
+    (2.08, 0.108, 1.0, 0.1),     # d = 0.449: Poisson mixture
+    (0.1, 0.5, 1.0, 0.05),       # d = 0.1: Poisson mixture, boosted gamma when N = 0
+])
+def test_native_one_step_is_the_exact_cir_transition(k, theta, sigma, v0):
+    """One step of the native sampler against the exact law of the CIR transition,
+    V' = (c / 2) * noncentral-chi-square(df = 2 d, nc = 2 lc V_0)  (NMCH_EM.cu:226-241 in distribution).
+    Kolmogorov-Smirnov on 2^18 paths, two consecutive calls (two streams)."""
+    from scipy import stats
+    n, dt = 1 << 18, 1e-3
+    e_kdt = np.exp(-k * dt)
+    c = sigma * sigma * (1.0 - e_kdt) / (2.0 * k)
+    d = 2.0 * k * theta / (sigma * sigma)
+    lc = 2.0 * k * e_kdt / (sigma * sigma * (1.0 - e_kdt))
+    law = stats.ncx2(df=2.0 * d, nc=2.0 * lc * v0, scale=0.5 * c)
+    with em_engine(n, 1, rng=0, k=k, theta=theta, sigma=sigma, v_0=v0, T=dt) as e:
+        e.init(2024)
+        for _ in range(2):
+            _, V, _ = e.compute_paths()
+            V = V.astype(np.float64)
+            assert np.isfinite(V).all() and (V >= 0).all()
+            ks = stats.kstest(V, law.cdf)
+            assert ks.pvalue > 1e-3, (ks, V.mean(), law.mean())
+            assert abs(V.mean() - law.mean()) < 4.5 * law.std() / np.sqrt(n)
+
+
 @pytest.mark.parametrize("k,theta,sigma,want", [
     (2.08, 0.108, 1.0, 0.1104934558),     # d = 0.449 < 1/2: Poisson-mixture path (PTRS + inversion)
     (10.0, 0.5, 1.0, 0.2607554745),       # d = 10: chi-square split, no boost
