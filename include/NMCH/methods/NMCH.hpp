@@ -40,6 +40,12 @@ public:
     void set_philox_dense(bool on) { philox_dense = on; }         // Philox tag, FE only (ignored otherwise): 3 steps per Philox block (+15 %, own mapping)
     void set_xorwow_fast(bool on) { xorwow_fast = on; }           // XORWOW tag, FE only (ignored otherwise): cuRAND's integer draws, native fast-math step
     void set_paths_per_thread(int p) { paths_per_thread = p; }
+    /* Exact legacy output of the reference's K1 kernels (FE_k1 / EM_k1, reference NMCH_FE.cu:56-58, NMCH_EM.cu:129-131):
+       they reduce (payoff/n)^2/n, so get_price_squared() of the *_K1* classes (K1_MM, K1_PgM, K1_PiM; not K2 / K3)
+       returns E[X^2]/n^2 there.  Off by default (every class stores E[X^2]); on, the K1 classes reproduce the quirk --
+       and with it the reference's get_err() and print_stats() lines, which are computed from that field.
+       No effect on the K2 / K3 classes.  May be called at any time; acts at the next compute(). */
+    void set_legacy_k1_moment(bool on) { legacy_k1_moment = on; }
     /* raw FP64 sums behind strike_price / price_squared, and the plain standard error of the mean */
     double get_sum_payoff() const { return sum_payoff; }
     double get_sum_payoff_sq() const { return sum_payoff_sq; }
@@ -79,11 +85,13 @@ protected:
     nmch_group_t *group = nullptr;
     double sum_payoff = 0.0, sum_payoff_sq = 0.0;
     bool floor_plus = false, philox_compat = false, philox_dense = false, xorwow_fast = false;
+    bool legacy_k1_moment = false;
     int gpus = 1, paths_per_thread = 0;
 
     void engine_init(int method, unsigned long long seed, float *tim_init);
     void engine_compute(float *tim_exec);
     void engine_finalize();
+    void apply_legacy_k1_moment();   /* called by the classes that stand for the reference's K1 kernels */
     unsigned long long path_count() const { return (unsigned long long)NTPB * (unsigned long long)NB; }
 };
 

@@ -3,7 +3,8 @@
 // (managed / pageable / pinned), reduction (shared-memory tree vs warp shuffle) and where the cuRAND state
 // lives; here every name maps to the one fused sm_100a kernel, whose result does not depend on those choices.
 // One documented difference: the reference's K1 classes store E[X^2]/n^2 in price_squared by accident
-// (NMCH_FE.cu:56-58); all classes here store E[X^2], like its K2/K3 classes.
+// (NMCH_FE.cu:56-58); by default all classes here store E[X^2], like its K2/K3 classes, and
+// set_legacy_k1_moment(true) makes the K1 classes reproduce the reference's value exactly.
 #ifndef NMCH_FW_EULER_HPP
 #define NMCH_FW_EULER_HPP
 

@@ -98,7 +98,10 @@ int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out);
 int nmch_engine_compute_async(nmch_engine_t *e, void *cuda_stream, double *d_moments);
 /* The exploration sweep of src/NMCH/test/exploration.cu:71-88 as ONE launch: point i uses
  * (k[i], theta[i], sigma[i]) and the stream position it would have had after i sequential compute()
- * calls, so explore() equals n_points x { set_params; compute } bit for bit. out has n_points entries. */
+ * calls, so explore() uses the same draws as n_points x { set_params; compute } and returns the same sums up to
+ * the order of the FP64 summation (bit for bit when the two launches have the same shape: paths per thread and
+ * tiles per block are picked from n_local x n_points).  out has n_points entries.  EM sweeps whose points need
+ * different variance samplers (d = 2 k theta / sigma^2 below 1/2, between 1/2 and 3/2, above) are still ONE launch. */
 int nmch_engine_explore(nmch_engine_t *e, const float *k, const float *theta, const float *sigma,
                         int n_points, nmch_moments_t *out);
 int nmch_engine_explore_async(nmch_engine_t *e, void *cuda_stream, const float *k, const float *theta,
@@ -129,6 +132,17 @@ int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const
 /* finalize() (NMCH_FE.cu:326-331); idempotent here (the reference double-frees) */
 int nmch_engine_finalize(nmch_engine_t *e);
 void nmch_engine_destroy(nmch_engine_t *e);
+
+/* Memory-safety probe (no reference equivalent; its only check is one testCUDA, NMCH_FE.cu:685).  Synchronises the
+ * device and, in the checked build of this library (libnmch_b200_checked.so: -DNMCHB_CHECKS, device-side asserts on
+ * every index the kernels form + guard bands around every device buffer), sweeps the guard bands: NMCH_ERR_CUDA names
+ * the buffer a kernel wrote outside of, or reports the failed device assert.  The blocking entry points run the same
+ * sweep themselves; this call is for *_async users.  In the normal build it is a synchronise that returns NMCH_OK.
+ * nmch_checked_build() tells which build is loaded. */
+int nmch_engine_check(nmch_engine_t *e);
+int nmch_checked_build(void);
+/* checked build only: plants an overrun behind the ticket array and verifies that the sweep reports it (NMCH_OK = it did) */
+int nmch_checked_selftest(nmch_engine_t *e);
 
 /* Tim_init (NMCH_FE.cu:370-385) and launch facts for reports */
 float nmch_engine_init_ms(const nmch_engine_t *e);

@@ -13,6 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnmch_b200.so")
+LIB_CHECKED = os.path.join(PKG, "libnmch_b200_checked.so")     # -DNMCHB_CHECKS: device asserts + guard bands
 BIN = os.path.join(ROOT, "bin")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -62,6 +63,33 @@ def build(force: bool = False, verbose: bool = False, only_if_missing: bool = Fa
     return LIB
 
 
+def build_checked(force: bool = False, verbose: bool = False, only_if_missing: bool = False) -> str:
+    """The checked build of the same sources and ABI (nmch_b200/libnmch_b200_checked.so): -DNMCHB_CHECKS turns on the
+    device-side asserts and puts guard bands around every device buffer (csrc/device_common.cuh, csrc/engine.cu).
+    It stands in for compute-sanitizer, which is closed on the B200 pool; tests/test_gpu_checked_build.py loads it
+    through NMCH_B200_LIB and runs the ragged / 64-bit-index / shard / multi-tile cases."""
+    if only_if_missing and os.path.exists(LIB_CHECKED):
+        return LIB_CHECKED
+    if force or _newer(LIB_CHECKED, _deps()):
+        out_dir = os.path.join(PKG, "build", "checked")
+        os.makedirs(out_dir, exist_ok=True)
+        objs = []
+        for src in CU_SOURCES:
+            obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+            if force or _newer(obj, _deps()):
+                cmd = [NVCC, *ARCH, *COMMON, "-DNMCHB_CHECKS", "-I", os.path.join(ROOT, "include"), "-c",
+                       os.path.join(CSRC, src), "-o", obj]
+                if verbose:
+                    print(" ".join(cmd))
+                subprocess.run(cmd, check=True)
+            objs.append(obj)
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB_CHECKED, *objs, "-ldl"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB_CHECKED
+
+
 def build_cli(force: bool = False, verbose: bool = False, only_if_missing: bool = False):
     """Compile the C++ method API + the NMCH / exploration CLIs (host C++ over the C ABI)."""
     build(force=force, verbose=verbose, only_if_missing=only_if_missing)
@@ -95,4 +123,5 @@ def build_cli(force: bool = False, verbose: bool = False, only_if_missing: bool 
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_checked(force="--force" in sys.argv, verbose=True))
     print(build_cli(force="--force" in sys.argv, verbose=True))

@@ -44,7 +44,7 @@ EXPORTS = [
     "nmch_engine_create", "nmch_engine_init", "nmch_engine_set_params", "nmch_engine_seek", "nmch_engine_compute",
     "nmch_engine_compute_async", "nmch_engine_explore", "nmch_engine_explore_async",
     "nmch_engine_compute_paths", "nmch_engine_compute_strikes", "nmch_engine_compute_strikes_async",
-    "nmch_engine_finalize", "nmch_engine_destroy", "nmch_engine_init_ms",
+    "nmch_engine_finalize", "nmch_engine_destroy", "nmch_engine_init_ms", "nmch_engine_check", "nmch_checked_build", "nmch_checked_selftest",
     "nmch_engine_launch_info", "nmch_group_create", "nmch_group_init", "nmch_group_set_params", "nmch_group_compute",
     "nmch_group_explore", "nmch_group_compute_strikes", "nmch_group_finalize", "nmch_group_destroy", "nmch_group_init_ms", "nmch_group_size",
     "nmch_status_string", "nmch_last_error", "nmch_device_count", "nmch_version",
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     L.nmch_engine_compute_strikes.argtypes = [vp, f32p, C.c_int, C.POINTER(NmchStrikeMoments)]
     L.nmch_engine_compute_strikes_async.argtypes = [vp, vp, f32p, C.c_int, vp]
     L.nmch_group_compute_strikes.argtypes = [vp, f32p, C.c_int, C.POINTER(NmchStrikeMoments)]
+    L.nmch_engine_check.argtypes = [vp]
+    L.nmch_checked_selftest.argtypes = [vp]
     L.nmch_engine_finalize.argtypes = [vp]
     L.nmch_engine_destroy.argtypes = [vp]
     L.nmch_engine_destroy.restype = None

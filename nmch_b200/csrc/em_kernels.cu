@@ -548,7 +548,7 @@ template <typename State>
 static int curand_states_init(nmch_engine *e)
 {
     const size_t n = (size_t)e->n_local;
-    cudaError_t err = cudaMalloc(&e->curand_states, n * sizeof(State));
+    cudaError_t err = engine_dev_malloc(e, &e->curand_states, n * sizeof(State), "cuRAND-layout states");
     if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "cudaMalloc(cuRAND-layout states)", err);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     curand_state_init_kernel<State><<<blocks, 256, 0, e->stream>>>(static_cast<State *>(e->curand_states), e->seed,
@@ -564,7 +564,7 @@ int mrg_compat_init(nmch_engine *e) { return curand_states_init<curandStateMRG32
 
 void em_release(nmch_engine *e)
 {
-    if (e->curand_states) cudaFree(e->curand_states);
+    engine_dev_free(e, e->curand_states);
     e->curand_states = nullptr;
 }
 

@@ -38,6 +38,64 @@ int engine_fail(int status, const char *what, cudaError_t err)
     return status;
 }
 }  // namespace nmchb
+namespace nmchb {
+#ifdef NMCHB_CHECKS
+constexpr size_t kGuardBytes = 256;
+constexpr int kGuardByte = 0xA5;
+
+cudaError_t engine_dev_malloc(nmch_engine *e, void **ptr, size_t bytes, const char *name)
+{
+    *ptr = nullptr;
+    unsigned char *base = nullptr;
+    const size_t padded = (bytes + 255) / 256 * 256;         // keep the user pointer and the tail guard 256-byte aligned
+    cudaError_t err = cudaMalloc(&base, padded + 2 * kGuardBytes);
+    if (err != cudaSuccess) return err;
+    err = cudaMemset(base, kGuardByte, padded + 2 * kGuardBytes);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { cudaFree(base); return err; }
+    *ptr = base + kGuardBytes;
+    e->guarded.push_back(nmch_guarded_alloc{base, *ptr, bytes, name});
+    return cudaSuccess;
+}
+
+void engine_dev_free(nmch_engine *e, void *ptr)
+{
+    if (!ptr) return;
+    for (size_t i = 0; i < e->guarded.size(); ++i)
+        if (e->guarded[i].user == ptr) {
+            cudaFree(e->guarded[i].base);
+            e->guarded.erase(e->guarded.begin() + (long)i);
+            return;
+        }
+    cudaFree(ptr);
+}
+
+int engine_check_guards(nmch_engine *e)
+{
+    std::vector<unsigned char> host(2 * kGuardBytes + 256);
+    for (const nmch_guarded_alloc &g : e->guarded) {
+        const unsigned char *base = static_cast<const unsigned char *>(g.base);
+        const size_t tail_off = kGuardBytes + g.bytes;                       // first byte past the user's bytes
+        const size_t tail_len = (g.bytes + 255) / 256 * 256 - g.bytes + kGuardBytes;
+        cudaError_t err = cudaMemcpy(host.data(), base, kGuardBytes, cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess) err = cudaMemcpy(host.data() + kGuardBytes, base + tail_off, tail_len, cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "guard sweep", err);
+        for (size_t i = 0; i < kGuardBytes + tail_len; ++i)
+            if (host[i] != (unsigned char)kGuardByte) {
+                char buf[160];
+                std::snprintf(buf, sizeof buf, "checked build: guard band of device buffer '%s' (%zu bytes) overwritten %s it",
+                              g.name, g.bytes, i < kGuardBytes ? "before" : "after");
+                return engine_fail(NMCH_ERR_CUDA, buf);
+            }
+    }
+    return NMCH_OK;
+}
+#else
+cudaError_t engine_dev_malloc(nmch_engine *, void **ptr, size_t bytes, const char *) { return cudaMalloc(ptr, bytes); }
+void engine_dev_free(nmch_engine *, void *ptr) { if (ptr) cudaFree(ptr); }
+int engine_check_guards(nmch_engine *) { return NMCH_OK; }
+#endif
+}  // namespace nmchb
 namespace {
 inline int fail(int status, const char *what, cudaError_t err = cudaSuccess) { return engine_fail(status, what, err); }
 
@@ -117,6 +175,8 @@ void fill_fe_launch(const nmch_engine *e, FeLaunch &L, int n_points, int blocks_
     L.n_points = n_points;
     L.blocks_per_point = blocks_per_point;
     L.tiles_per_block = tiles_per_block;
+    L.chunk_points = n_points;
+    L.n_chunks = 1;
     L.S0 = p.S_0;
     L.v0 = p.v_0;
     L.K = p.S_0;                                             // at the money, NMCH.cu:7
@@ -136,18 +196,21 @@ int ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, siz
 {
     const size_t need_partials = n_points * blocks_per_point;
     if (need_partials > e->partials_cap) {
-        if (e->d_partials) cudaFree(e->d_partials);
+        engine_dev_free(e, e->d_partials);
         e->d_partials = nullptr;
         e->partials_cap = 0;
-        CU_TRY(cudaMalloc(&e->d_partials, need_partials * sizeof(double2)));
+        CU_TRY(engine_dev_malloc(e, (void **)&e->d_partials, need_partials * sizeof(double2), "partials"));
         e->partials_cap = need_partials;
     }
     if (n_points > e->tickets_cap) {
-        if (e->d_tickets) cudaFree(e->d_tickets);
+        engine_dev_free(e, e->d_tickets);
         e->d_tickets = nullptr;
         e->tickets_cap = 0;
-        CU_TRY(cudaMalloc(&e->d_tickets, n_points * sizeof(unsigned int)));
-        CU_TRY(cudaMemset(e->d_tickets, 0, n_points * sizeof(unsigned int)));   // blocking: the next launch may be on any stream
+        CU_TRY(engine_dev_malloc(e, (void **)&e->d_tickets, n_points * sizeof(unsigned int), "tickets"));
+        // The next launch may be on any stream (the engine's, a group stream, a caller's -- all non-blocking, i.e. not
+        // ordered against the legacy default stream the memset runs on): wait for it on the host before anyone launches.
+        CU_TRY(cudaMemsetAsync(e->d_tickets, 0, n_points * sizeof(unsigned int), 0));
+        CU_TRY(cudaStreamSynchronize(0));
         e->tickets_cap = n_points;
     }
     if (2 * n_points > e->out_cap) {
@@ -159,10 +222,10 @@ int ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, siz
         e->out_cap = 2 * n_points;
     }
     if (point_bytes > e->points_cap) {
-        if (e->d_points) cudaFree(e->d_points);
+        engine_dev_free(e, e->d_points);
         e->d_points = nullptr;
         e->points_cap = 0;
-        CU_TRY(cudaMalloc(&e->d_points, point_bytes));
+        CU_TRY(engine_dev_malloc(e, &e->d_points, point_bytes, "points"));
         e->points_cap = point_bytes;
     }
     return NMCH_OK;
@@ -171,12 +234,12 @@ int ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, siz
 int ensure_sv(nmch_engine *e, size_t count)
 {
     if (count > e->sv_cap) {
-        if (e->d_S) cudaFree(e->d_S);
-        if (e->d_V) cudaFree(e->d_V);
+        engine_dev_free(e, e->d_S);
+        engine_dev_free(e, e->d_V);
         e->d_S = e->d_V = nullptr;
         e->sv_cap = 0;
-        CU_TRY(cudaMalloc(&e->d_S, count * sizeof(float)));
-        CU_TRY(cudaMalloc(&e->d_V, count * sizeof(float)));
+        CU_TRY(engine_dev_malloc(e, (void **)&e->d_S, count * sizeof(float), "S_T"));
+        CU_TRY(engine_dev_malloc(e, (void **)&e->d_V, count * sizeof(float), "V_T"));
         e->sv_cap = count;
     }
     return NMCH_OK;
@@ -189,6 +252,40 @@ static int validate_point(int method, float k, float theta, float sigma, float v
     const bool ok = std::isfinite(k) && std::isfinite(theta) && std::isfinite(sigma) && k > 0.0f && sigma > 0.0f &&
                     theta >= 0.0f && v0 >= 0.0f;
     return ok ? NMCH_OK : fail(NMCH_ERR_ARG, "EM / QE need k > 0, sigma > 0, theta >= 0, v_0 >= 0 (finite)");
+}
+
+// A sweep on a sequential XORWOW stream walks its points inside the thread.  When the paths alone cannot fill the GPU
+// (the reference's own exploration: 5120 paths x 200 points, exploration.cu:24-25) the walk is cut into chunks of
+// consecutive points, one grid.y slice each, started by skipping chunk * chunk_points * 2N draws ahead.
+int plan_xorwow_chunks(nmch_engine *e, cudaStream_t stream, int n_points, FeLaunch &L, const uint32_t **skip)
+{
+    L.chunk_points = n_points;
+    L.n_chunks = 1;
+    *skip = nullptr;
+    const unsigned long long target = (unsigned long long)(e->sm_count > 0 ? e->sm_count : 148) * 1536ull;   // threads that fill the GPU
+    if (n_points < 2 || e->n_local >= target) return NMCH_OK;
+    unsigned long long want = (target + e->n_local - 1ull) / e->n_local;
+    if (want > (unsigned long long)n_points) want = (unsigned long long)n_points;
+    L.chunk_points = (int)(((unsigned long long)n_points + want - 1ull) / want);
+    L.n_chunks = (n_points + L.chunk_points - 1) / L.chunk_points;
+    if (L.n_chunks < 2) return NMCH_OK;
+    const unsigned long long draws = 2ull * (unsigned long long)e->p.N * (unsigned long long)L.chunk_points;
+    int digits = 0;
+    for (unsigned int c = (unsigned int)(L.n_chunks - 1); c != 0u; c >>= 2) ++digits;
+    if (!e->d_xskip || e->xskip_draws != draws || e->xskip_digits < digits) {
+        const std::vector<uint32_t> host = xorwow_offset_tables_host(draws, digits);
+        engine_dev_free(e, e->d_xskip);
+        e->d_xskip = nullptr;
+        e->xskip_draws = 0;
+        e->xskip_digits = 0;
+        CU_TRY(engine_dev_malloc(e, (void **)&e->d_xskip, host.size() * sizeof(uint32_t), "xorwow offset-skip tables"));
+        CU_TRY(cudaMemcpyAsync(e->d_xskip, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        CU_TRY(cudaStreamSynchronize(stream));                 // `host` is a local
+        e->xskip_draws = draws;
+        e->xskip_digits = digits;
+    }
+    *skip = e->d_xskip;
+    return NMCH_OK;
 }
 
 // One launch over n_points parameter points.  k/theta/sigma are HOST arrays (nullptr => the engine's own
@@ -253,7 +350,10 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                 d_pts = static_cast<const FePoint *>(e->d_points);
             }
             ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
-            CU_TRY(launch_fe_xorwow_fast(L, p.floor, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
+            const uint32_t *skip = nullptr;
+            rc = plan_xorwow_chunks(e, stream, n_points, L, &skip);
+            if (rc) return rc;
+            CU_TRY(launch_fe_xorwow_fast(L, p.floor, d_pts, e->xs, skip, rb, S_out, V_out, stream, &e->kinfo));
         } else {
             const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
             if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
@@ -269,10 +369,14 @@ int launch_points(nmch_engine *e, cudaStream_t stream, const float *k, const flo
                 d_pts = static_cast<const RawPoint *>(e->d_points);
             }
             ReduceBuffers rb{e->d_partials, e->d_tickets, d_out};
-            if (p.rng == NMCH_RNG_MRG32K3A_COMPAT)
+            if (p.rng == NMCH_RNG_MRG32K3A_COMPAT) {
                 CU_TRY(launch_fe_compat_mrg(L, p.floor, d_pts, e->curand_states, rb, S_out, V_out, stream, &e->kinfo));
-            else
-                CU_TRY(launch_fe_compat(L, p.floor, d_pts, e->xs, rb, S_out, V_out, stream, &e->kinfo));
+            } else {
+                const uint32_t *skip = nullptr;
+                rc = plan_xorwow_chunks(e, stream, n_points, L, &skip);
+                if (rc) return rc;
+                CU_TRY(launch_fe_compat(L, p.floor, d_pts, e->xs, skip, rb, S_out, V_out, stream, &e->kinfo));
+            }
         }
         e->draw_offset += 2ull * (unsigned long long)p.N * (unsigned long long)n_points;
     } else if (p.method == NMCH_METHOD_EM) {
@@ -398,14 +502,14 @@ static int engine_init_impl(nmch_engine_t *e, unsigned long long seed)
         const size_t n = (size_t)e->n_local;
         CU_TRY(xorwow_tables_create(&e->xtab));
         uint32_t *base = nullptr;
-        CU_TRY(cudaMalloc(&base, 6 * n * sizeof(uint32_t)));
+        CU_TRY(engine_dev_malloc(e, (void **)&base, 6 * n * sizeof(uint32_t), "xorwow states"));
         e->xs.d = base; e->xs.v0 = base + n; e->xs.v1 = base + 2 * n;
         e->xs.v2 = base + 3 * n; e->xs.v3 = base + 4 * n; e->xs.v4 = base + 5 * n;
         if (e->p.method == NMCH_METHOD_EM) {
-            CU_TRY(cudaMalloc(&e->xs.bm_flag, n * sizeof(int)));
-            CU_TRY(cudaMalloc(&e->xs.bm_extra, n * sizeof(float)));
-            CU_TRY(cudaMalloc(&e->xs.bm_flag_d, n * sizeof(int)));
-            CU_TRY(cudaMalloc(&e->xs.bm_extra_d, n * sizeof(double)));
+            CU_TRY(engine_dev_malloc(e, (void **)&e->xs.bm_flag, n * sizeof(int), "xorwow bm_flag"));
+            CU_TRY(engine_dev_malloc(e, (void **)&e->xs.bm_extra, n * sizeof(float), "xorwow bm_extra"));
+            CU_TRY(engine_dev_malloc(e, (void **)&e->xs.bm_flag_d, n * sizeof(int), "xorwow bm_flag_d"));
+            CU_TRY(engine_dev_malloc(e, (void **)&e->xs.bm_extra_d, n * sizeof(double), "xorwow bm_extra_d"));
         }
         CU_TRY(launch_xorwow_init(e->xtab, seed, e->first_path, e->n_local, e->xs, e->stream));
         e->launches += 1;
@@ -422,7 +526,7 @@ static int engine_init_impl(nmch_engine_t *e, unsigned long long seed)
     CU_TRY(cudaEventSynchronize(e->ev1));
     CU_TRY(cudaEventElapsedTime(&e->init_ms, e->ev0, e->ev1));
     e->inited = true;
-    return NMCH_OK;
+    return engine_check_guards(e);
 }
 
 int nmch_engine_set_params(nmch_engine_t *e, float k, float theta, float sigma)
@@ -464,7 +568,7 @@ int nmch_engine_compute(nmch_engine_t *e, nmch_moments_t *out)
     float ms = 0.0f;
     CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     fill_moments(e, e->h_out, 1, ms, out);
-    return NMCH_OK;
+    return engine_check_guards(e);
 }
 
 int nmch_engine_compute_async(nmch_engine_t *e, void *cuda_stream, double *d_moments)
@@ -498,7 +602,7 @@ int nmch_engine_explore(nmch_engine_t *e, const float *k, const float *theta, co
     float ms = 0.0f;
     CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     fill_moments(e, e->h_out, n_points, ms, out);
-    return NMCH_OK;
+    return engine_check_guards(e);
 }
 
 int nmch_engine_explore_async(nmch_engine_t *e, void *cuda_stream, const float *k, const float *theta,
@@ -537,7 +641,7 @@ int nmch_engine_compute_paths(nmch_engine_t *e, float *S_out, float *V_out, unsi
     float ms = 0.0f;
     CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     fill_moments(e, e->h_out, 1, ms, out);
-    return NMCH_OK;
+    return engine_check_guards(e);
 }
 
 // shared by the blocking and the stream form: path kernel (keeps S_T on the device) + strike kernel
@@ -586,7 +690,7 @@ int nmch_engine_compute_strikes(nmch_engine_t *e, const float *strikes, int n_st
         out[j].n_paths = e->n_local;
         out[j].exec_ms = ms;
     }
-    return NMCH_OK;
+    return engine_check_guards(e);
 }
 
 int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const float *strikes, int n_strikes,
@@ -607,17 +711,21 @@ int nmch_engine_finalize(nmch_engine_t *e)
     // every resource is released if present, whatever the lifecycle flag says.
     DeviceGuard guard(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->d_partials) cudaFree(e->d_partials);
-    if (e->d_tickets) cudaFree(e->d_tickets);
+    engine_dev_free(e, e->d_partials);
+    engine_dev_free(e, e->d_tickets);
     if (e->h_out) cudaFreeHost(e->h_out);
-    if (e->d_points) cudaFree(e->d_points);
-    if (e->d_S) cudaFree(e->d_S);
-    if (e->d_V) cudaFree(e->d_V);
-    if (e->xs.d) cudaFree(e->xs.d);
-    if (e->xs.bm_flag) cudaFree(e->xs.bm_flag);
-    if (e->xs.bm_extra) cudaFree(e->xs.bm_extra);
-    if (e->xs.bm_flag_d) cudaFree(e->xs.bm_flag_d);
-    if (e->xs.bm_extra_d) cudaFree(e->xs.bm_extra_d);
+    engine_dev_free(e, e->d_points);
+    engine_dev_free(e, e->d_S);
+    engine_dev_free(e, e->d_V);
+    engine_dev_free(e, e->xs.d);
+    engine_dev_free(e, e->xs.bm_flag);
+    engine_dev_free(e, e->xs.bm_extra);
+    engine_dev_free(e, e->xs.bm_flag_d);
+    engine_dev_free(e, e->xs.bm_extra_d);
+    engine_dev_free(e, e->d_xskip);
+    e->d_xskip = nullptr;
+    e->xskip_draws = 0;
+    e->xskip_digits = 0;
     em_release(e);
     xorwow_tables_destroy(e->xtab);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -641,6 +749,47 @@ void nmch_engine_destroy(nmch_engine_t *e)
     if (!e) return;
     nmch_engine_finalize(e);
     delete e;
+}
+
+int nmch_engine_check(nmch_engine_t *e)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    CU_TRY(cudaDeviceSynchronize());               // *_async work may sit on caller streams: a device assert surfaces here
+    return engine_check_guards(e);
+}
+
+int nmch_checked_selftest(nmch_engine_t *e)
+{
+#ifdef NMCHB_CHECKS
+    // Proves the guard sweep sees an overrun: write one word past the ticket array (what an off-by-one point index
+    // would do), expect the sweep to fail naming "tickets", then repair the band.
+    int rc = check_ready(e);
+    if (rc) return rc;
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    const unsigned int junk = 0xdeadbeefu;
+    unsigned char *past = reinterpret_cast<unsigned char *>(e->d_tickets) + e->tickets_cap * sizeof(unsigned int);
+    CU_TRY(cudaMemcpy(past, &junk, sizeof junk, cudaMemcpyHostToDevice));
+    const int seen = engine_check_guards(e);
+    CU_TRY(cudaMemset(past, kGuardByte, sizeof junk));
+    if (seen == NMCH_OK) return fail(NMCH_ERR_STATE, "checked build: the guard sweep missed a deliberate overrun");
+    return engine_check_guards(e);                 // clean again after the repair
+#else
+    (void)e;
+    return fail(NMCH_ERR_STATE, "not a checked build (load libnmch_b200_checked.so)");
+#endif
+}
+
+int nmch_checked_build(void)
+{
+#ifdef NMCHB_CHECKS
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 float nmch_engine_init_ms(const nmch_engine_t *e) { return e ? e->init_ms : 0.0f; }

@@ -1,8 +1,18 @@
 // engine_internal.cuh -- the engine object behind the opaque nmch_engine_t handle, shared by engine.cu
 // (FE + lifecycle) and em_kernels.cu (EM launches).
 #pragma once
+#include <vector>
+
 #include "../../include/nmch_b200.h"
 #include "kernels.cuh"
+
+// one device allocation of an engine in the checked build: [guard | user bytes | guard]
+struct nmch_guarded_alloc {
+    void *base;
+    void *user;
+    size_t bytes;
+    const char *name;
+};
 
 struct nmch_engine {
     nmch_params_t p{};
@@ -32,14 +42,24 @@ struct nmch_engine {
     // XORWOW-compat state
     nmchb::XorwowSkipTables *xtab = nullptr;
     nmchb::XorwowState xs{};
+    uint32_t *d_xskip = nullptr;             // XORWOW offset-skip tables of the current sweep shape (chunked sweeps)
+    unsigned long long xskip_draws = 0;      //   ... for chunks of this many draws
+    int xskip_digits = 0;                    //   ... and this many base-4 digits of the chunk index
     void *curand_states = nullptr;           // cuRAND-layout states (AoS): Philox-compat EM, MRG32k3a-compat FE/EM
     nmchb::KernelInfo kinfo{};
     unsigned long long launches = 0;
+    std::vector<nmch_guarded_alloc> guarded;  // checked build (-DNMCHB_CHECKS) only: every device buffer, for the guard sweep
 };
 
 namespace nmchb {
 
 int engine_fail(int status, const char *what, cudaError_t err = cudaSuccess);
+// Device memory of an engine.  Normal build: cudaMalloc / cudaFree.  Checked build: each buffer sits between two guard
+// bands filled with a pattern, and engine_check_guards() (run by every blocking entry point after its sync, and by
+// nmch_engine_check) fails with NMCH_ERR_CUDA naming the buffer whose band a kernel overwrote.
+cudaError_t engine_dev_malloc(nmch_engine *e, void **ptr, size_t bytes, const char *name);
+void engine_dev_free(nmch_engine *e, void *ptr);
+int engine_check_guards(nmch_engine *e);
 int engine_ensure_buffers(nmch_engine *e, size_t n_points, size_t blocks_per_point, size_t point_bytes);
 
 // em_kernels.cu

@@ -8,13 +8,14 @@
 // Native kernel, per path-step (see DESIGN.md §Kernels for the instruction budget):
 //   * half a Philox4x32-10 block (the block serves two steps; round keys sit in uniform registers, the
 //     counter-invariant part of rounds 1-2 is hoisted per path)
-//   * u32 -> float by bit splicing (ALU pipe, no I2F on the XU pipe)
+//   * u32 -> float with I2FP (ALU pipe; not the XU-pipe I2F) + one FFMA: cuRAND's own uniforms
 //   * Box-Muller with MUFU.LG2 / MUFU.SIN / MUFU.COS and ONE MUFU.SQRT shared with the SDE:
 //       sqrt(V)*sqrt(-2 ln u) = c0 * sqrt(-V * lg2 u),  c0 = sqrt(2 ln 2) folded into host constants
 //   * S' = S + S * (r dt + q sin * zr + q cos * zc),  V' = g(V*va + vb + q sin * vs)
 //   state (S, V, counters) stays in registers for all N steps: zero HBM traffic in the loop.
 #include "compat_math.cuh"
 #include "kernels.cuh"
+#include "xorwow_device.cuh"
 
 namespace nmchb {
 
@@ -30,21 +31,16 @@ template <int FLOOR, bool PRECISE_V = false>
 __device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, uint32_t wb, float rdt,
                                                float zr, float zc, const FePoint &pc)
 {
-#ifdef NMCHB_FE_I2FP
-    // tuning variant: integer -> float conversion (I2FP) instead of bit splicing; the uniforms are then cuRAND's own
-    // (x * 2^-32 + 2^-33, curand_uniform.h:69-72), 24 bits, in (0, 1]
-    const float u = fmaf(__uint2float_rn(wa), 2.3283064e-10f, 1.1641532e-10f);
+    // uniforms as cuRAND forms them (curand_uniform.h:69-72, curand_normal.h:72-75): u = x 2^-32 + 2^-33 in (0, 1],
+    // angle = y (2 pi 2^-32) -- an integer-to-float conversion (I2FP) and one FFMA / FMUL.  Against bit
+    // splicing ((w >> 9) | 0x3f800000, then a subtraction) this costs the same instruction count, but I2FP issues beside
+    // the FP32 work where LEA.HI does not (profiles/r02_pipe_rates2.txt: -1 % on the kernel), and the native mode now
+    // feeds the same uniforms as the draw-compatible modes into its fast transforms.
+    constexpr float k2Pow32Inv = 2.3283064e-10f, k2Pow32Inv2Pi = 2.3283064e-10f * 6.2831855f;
+    const float u = fmaf(__uint2float_rn(wa), k2Pow32Inv, k2Pow32Inv * 0.5f);
     const float l2 = lg2_approx(u);                   // <= 0
     const float q = sqrt_approx(-(V * l2));           // sqrt(V) * sqrt(-lg2 u)
-    const float ang = __uint2float_rn(wb) * 1.4629181e-9f;   // 2 pi 2^-32
-#else
-    const float f1 = bits_to_1_2(wa);
-    const float f2 = bits_to_1_2(wb);
-    const float u = f1 - 0.99999994f;                 // (floor(wa/2^9) + 0.5) * 2^-23, in (0,1): exact
-    const float l2 = lg2_approx(u);                   // < 0
-    const float q = sqrt_approx(-(V * l2));           // sqrt(V) * sqrt(-lg2 u)
-    const float ang = f2 * 6.2831855f;                // [2pi, 4pi): same sine/cosine as [0, 2pi)
-#endif
+    const float ang = __uint2float_rn(wb) * k2Pow32Inv2Pi;   // cuRAND adds half a step (7e-10 rad, below the angle's ulp)
     const float gs = q * sin_approx(ang);
     const float gc = q * cos_approx(ang);
     float m = fmaf(gs, zr, rdt);                      // relative increment; S' = S + S*m keeps r*dt at full precision
@@ -84,7 +80,10 @@ struct FeOccupancy {
 #ifndef NMCHB_FE_WARPS_P4
 #define NMCHB_FE_WARPS_P4 40
 #endif
-    static constexpr int kWarpsTarget = EXACT ? 32 : ((P <= 2) ? 48 : (P == 4 ? NMCHB_FE_WARPS_P4 : 24));
+    // P = 1 (30 registers) is what small launches get (engine.cu pick_paths_per_thread): 56 warps per SM = 14 blocks of
+    // 128 paths keep BASELINE configs[0] (2^18 paths = 13.8 blocks per SM) in ONE wave; with 12 resident blocks the
+    // last 272 of its 2048 blocks ran as a second, nearly empty wave (round 1: 0.66 of the roofline at that size).
+    static constexpr int kWarpsTarget = EXACT ? 32 : (P == 1 ? 56 : (P == 2 ? 48 : (P == 4 ? NMCHB_FE_WARPS_P4 : 24)));
     static constexpr int kMinBlocks = kWarpsTarget * 32 / THREADS;
 };
 
@@ -95,6 +94,8 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
 {
     constexpr int TILE = P * THREADS;
     const int point = blockIdx.y;
+    NMCHB_ASSERT(blockDim.x == THREADS && point < L.n_points && (int)blockIdx.x < L.blocks_per_point);
+    NMCHB_ASSERT(L.first_path % TILE == 0 && L.tiles_per_block >= 1);
     const FePoint pc = (pts != nullptr) ? pts[point] : (EXACT ? FePoint{L.raw0.k, L.raw0.theta, L.raw0.sigma, 0.0f} : L.pt0);
 
     // stream position of this point: what `point` sequential compute() calls would have consumed
@@ -111,6 +112,7 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
         const unsigned long long g0 = L.first_path + local0;     // multiple of TILE: no carry below
         const uint32_t path_hi = (uint32_t)(g0 >> 32);
         const uint32_t path_lo0 = (uint32_t)g0 + threadIdx.x;
+        NMCHB_ASSERT(((g0 + (unsigned long long)(TILE - 1)) >> 32) == (g0 >> 32));   // the tile's paths share path_hi
 
         float S[P], V[P];
 #pragma unroll
@@ -237,6 +239,8 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
 {
     constexpr int TILE = P * THREADS;
     const int point = blockIdx.y;
+    NMCHB_ASSERT(blockDim.x == THREADS && point < L.n_points && (int)blockIdx.x < L.blocks_per_point);
+    NMCHB_ASSERT(L.first_path % TILE == 0 && L.tiles_per_block >= 1 && L.dense_r0 < 3u && L.dense_rN < 3u);
     const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
     // stream position in STEPS (draw_offset counts two logical draws per step, like the other modes):
     //   s0 = draw_offset / 2 + point * N = 3 * blk0 + phase0, from the host's pre-divided parts -- a 64-bit division
@@ -247,6 +251,7 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
     const unsigned int q0 = (unsigned int)(((unsigned long long)t0 * 43691ull) >> 17);
     const unsigned long long blk0 = L.dense_q0 + (unsigned long long)point * (unsigned long long)L.dense_qN + (unsigned long long)q0;
     const int phase0 = (int)(t0 - 3u * q0);
+    NMCHB_ASSERT(phase0 >= 0 && phase0 < 3 && q0 == t0 / 3u);
 
     __shared__ double2 s_acc[THREADS];
     s_acc[threadIdx.x] = make_double2(0.0, 0.0);
@@ -431,23 +436,41 @@ struct CompatXorwow {
         d += 362437u;
         return v4 + d;
     }
+    // Start of chunk c of a sweep: c * chunk_points * 2N draws further down this path's stream.  FE consumes exactly 2N
+    // draws per point, so the position of every point is known in advance: the five xorshift words advance by the
+    // GF(2) matrix power A^c (A = T^(2N chunk_points), digit tables from the host), the Weyl word by a multiple.
+    __device__ __forceinline__ void skip_to_chunk(const uint32_t *__restrict__ tables, unsigned int c, uint32_t d_per_chunk)
+    {
+        uint32_t v[5] = {v0, v1, v2, v3, v4};
+        xorwow_apply_digits(v, tables, c);
+        v0 = v[0]; v1 = v[1]; v2 = v[2]; v3 = v[3]; v4 = v[4];
+        d += d_per_chunk * c;
+    }
 };
 
 template <int FLOOR>
 __global__ void __launch_bounds__(256)
 fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict__ pts, XorwowState xs,
-                 ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
+                 const uint32_t *__restrict__ skip, ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
 {
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
+    NMCHB_ASSERT((int)gridDim.x == L.blocks_per_point && (unsigned long long)gridDim.x * blockDim.x >= L.n_local);
+    NMCHB_ASSERT((int)gridDim.y == L.n_chunks && (L.n_chunks == 1 || skip != nullptr));
     CompatXorwow xw{};
     if (valid) {
         xw.d = xs.d[idx]; xw.v0 = xs.v0[idx]; xw.v1 = xs.v1[idx];
         xw.v2 = xs.v2[idx]; xw.v3 = xs.v3[idx]; xw.v4 = xs.v4[idx];
     }
-    // the points of a sweep are walked inside the thread: the XORWOW stream is sequential, and this is exactly the
-    // reference's order (one compute() after the other on the state written back by the previous one)
-    for (int point = 0; point < L.n_points; ++point) {
+    // The points of a sweep are walked inside the thread: the XORWOW stream is sequential, and this is exactly the
+    // reference's order (one compute() after the other on the state written back by the previous one).  When the
+    // paths alone cannot fill the GPU the walk is cut into chunks of consecutive points, blockIdx.y = chunk, each
+    // starting from the skipped-ahead state: same draws per (path, point), same blocks and reduction order per point.
+    const int chunk = blockIdx.y;
+    const int p0 = chunk * L.chunk_points;
+    const int p1 = min(p0 + L.chunk_points, L.n_points);
+    if (chunk > 0 && valid) xw.skip_to_chunk(skip, (unsigned int)chunk, 362437u * 2u * (uint32_t)L.N * (uint32_t)L.chunk_points);
+    for (int point = p0; point < p1; ++point) {
         const RawPoint rp = (pts != nullptr) ? pts[point] : L.raw0;
         float S = L.S0, V = L.v0;
         if (valid) {
@@ -471,8 +494,8 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
         block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x,
                                 L.blocks_per_point);
     }
-    if (valid) {                                 // streams continue across compute() calls (NMCH_FE.cu:303)
-        xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;
+    if (valid && chunk == L.n_chunks - 1) {      // streams continue across compute() calls (NMCH_FE.cu:303): the last
+        xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;     // chunk ends where the whole sweep ends
         xs.v2[idx] = xw.v2; xs.v3[idx] = xw.v3; xs.v4[idx] = xw.v4;
     }
 }
@@ -489,16 +512,22 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
 template <int FLOOR>
 __global__ void __launch_bounds__(256, 8)
 fe_xorwow_fast_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ pts, XorwowState xs,
-                      ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
+                      const uint32_t *__restrict__ skip, ReduceBuffers rb, float *__restrict__ S_out, float *__restrict__ V_out)
 {
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;
+    NMCHB_ASSERT((int)gridDim.x == L.blocks_per_point && (unsigned long long)gridDim.x * blockDim.x >= L.n_local);
+    NMCHB_ASSERT((int)gridDim.y == L.n_chunks && (L.n_chunks == 1 || skip != nullptr));
     CompatXorwow xw{};
     if (valid) {
         xw.d = xs.d[idx]; xw.v0 = xs.v0[idx]; xw.v1 = xs.v1[idx];
         xw.v2 = xs.v2[idx]; xw.v3 = xs.v3[idx]; xw.v4 = xs.v4[idx];
     }
-    for (int point = 0; point < L.n_points; ++point) {
+    const int chunk = blockIdx.y;                        // chunks of consecutive points, as in fe_compat_kernel
+    const int p0 = chunk * L.chunk_points;
+    const int p1 = min(p0 + L.chunk_points, L.n_points);
+    if (chunk > 0 && valid) xw.skip_to_chunk(skip, (unsigned int)chunk, 362437u * 2u * (uint32_t)L.N * (uint32_t)L.chunk_points);
+    for (int point = p0; point < p1; ++point) {
         const FePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
         float S = L.S0, V = L.v0;
         if (valid) {
@@ -520,50 +549,50 @@ fe_xorwow_fast_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restr
         block_reduce_and_finish(pay, pay * pay, rb.partials, rb.tickets, rb.out, point, blockIdx.x,
                                 L.blocks_per_point);
     }
-    if (valid) {                                 // streams continue across compute() calls (NMCH_FE.cu:303)
+    if (valid && chunk == L.n_chunks - 1) {      // streams continue across compute() calls (NMCH_FE.cu:303)
         xs.d[idx] = xw.d; xs.v0[idx] = xw.v0; xs.v1[idx] = xw.v1;
         xs.v2[idx] = xw.v2; xs.v3[idx] = xw.v3; xs.v4[idx] = xw.v4;
     }
 }
 
-cudaError_t launch_fe_xorwow_fast(const FeLaunch &L, int floor_kind, const FePoint *d_pts, XorwowState xs,
+cudaError_t launch_fe_xorwow_fast(const FeLaunch &L, int floor_kind, const FePoint *d_pts, XorwowState xs, const uint32_t *skip,
                                   ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
 {
     const int threads = 256;                 // one path per thread; L.blocks_per_point is sized for this
-    dim3 grid((unsigned)L.blocks_per_point, 1, 1);
+    dim3 grid((unsigned)L.blocks_per_point, (unsigned)L.n_chunks, 1);
     cudaFuncAttributes attr{};
     cudaError_t err = cudaSuccess;
     if (floor_kind == kFloorAbs) {
-        fe_xorwow_fast_kernel<kFloorAbs><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        fe_xorwow_fast_kernel<kFloorAbs><<<grid, threads, 0, stream>>>(L, d_pts, xs, skip, rb, S_out, V_out);
         err = cudaFuncGetAttributes(&attr, fe_xorwow_fast_kernel<kFloorAbs>);
     } else {
-        fe_xorwow_fast_kernel<kFloorPlus><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        fe_xorwow_fast_kernel<kFloorPlus><<<grid, threads, 0, stream>>>(L, d_pts, xs, skip, rb, S_out, V_out);
         err = cudaFuncGetAttributes(&attr, fe_xorwow_fast_kernel<kFloorPlus>);
     }
     if (info)
-        *info = KernelInfo{(int)grid.x, 1, threads, 1, attr.numRegs,
-                           (int)(sizeof(FeLaunch) + sizeof(const FePoint *) + sizeof(XorwowState) + sizeof(ReduceBuffers) + 2 * sizeof(float *))};
+        *info = KernelInfo{(int)grid.x, (int)grid.y, threads, 1, attr.numRegs,
+                           (int)(sizeof(FeLaunch) + sizeof(const FePoint *) + sizeof(XorwowState) + sizeof(ReduceBuffers) + 3 * sizeof(float *))};
     const cudaError_t lerr = cudaGetLastError();
     return lerr != cudaSuccess ? lerr : err;
 }
 
-cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,
+cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs, const uint32_t *skip,
                              ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info)
 {
     const int threads = 256;                 // one path per thread; L.blocks_per_point is sized for this
-    dim3 grid((unsigned)L.blocks_per_point, 1, 1);
+    dim3 grid((unsigned)L.blocks_per_point, (unsigned)L.n_chunks, 1);
     cudaFuncAttributes attr{};
     cudaError_t err = cudaSuccess;
     if (floor_kind == kFloorAbs) {
-        fe_compat_kernel<kFloorAbs><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        fe_compat_kernel<kFloorAbs><<<grid, threads, 0, stream>>>(L, d_pts, xs, skip, rb, S_out, V_out);
         err = cudaFuncGetAttributes(&attr, fe_compat_kernel<kFloorAbs>);
     } else {
-        fe_compat_kernel<kFloorPlus><<<grid, threads, 0, stream>>>(L, d_pts, xs, rb, S_out, V_out);
+        fe_compat_kernel<kFloorPlus><<<grid, threads, 0, stream>>>(L, d_pts, xs, skip, rb, S_out, V_out);
         err = cudaFuncGetAttributes(&attr, fe_compat_kernel<kFloorPlus>);
     }
     if (info) {
         info->grid_x = (int)grid.x;
-        info->grid_y = 1;
+        info->grid_y = (int)grid.y;
         info->block_threads = threads;
         info->paths_per_thread = 1;
         info->regs_per_thread = attr.numRegs;

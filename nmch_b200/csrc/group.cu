@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "engine_internal.cuh"
@@ -59,6 +60,19 @@ namespace {
 
 using nmchb::engine_fail;
 
+// restores the caller's current device on every exit path of a group call
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define GROUP_CU_TRY(call)                                                       \
+    do {                                                                         \
+        cudaError_t err__ = (call);                                              \
+        if (err__ != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, #call, err__); \
+    } while (0)
+
 int nccl_fail(const char *what, ncclResult_t r)
 {
     char buf[256];
@@ -70,8 +84,9 @@ int ensure_moments(nmch_group *g, size_t n_points)
 {
     const size_t need = 2 * n_points;
     if (need <= g->mom_cap) return NMCH_OK;
+    g->mom_cap = 0;
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
         if (g->d_mom[i]) cudaFree(g->d_mom[i]);
         g->d_mom[i] = nullptr;
         cudaError_t err = cudaMalloc(&g->d_mom[i], need * sizeof(double));
@@ -92,9 +107,8 @@ int run_points(nmch_group *g, const float *k, const float *theta, const float *s
     int rc = ensure_moments(g, (size_t)n_points);
     if (rc) return rc;
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
-        cudaError_t err = cudaEventRecord(g->ev0[i], g->stream[i]);
-        if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "cudaEventRecord", err);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+        GROUP_CU_TRY(cudaEventRecord(g->ev0[i], g->stream[i]));
         rc = k ? nmch_engine_explore_async(g->eng[i], g->stream[i], k, theta, sigma, n_points, g->d_mom[i])
                : nmch_engine_compute_async(g->eng[i], g->stream[i], g->d_mom[i]);
         if (rc) return rc;
@@ -111,16 +125,17 @@ int run_points(nmch_group *g, const float *k, const float *theta, const float *s
     }
     float ms = 0.0f;
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
-        if (i == 0) cudaMemcpyAsync(g->h_mom, g->d_mom[0], 2 * (size_t)n_points * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]);
-        cudaEventRecord(g->ev1[i], g->stream[i]);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+        if (i == 0)
+            GROUP_CU_TRY(cudaMemcpyAsync(g->h_mom, g->d_mom[0], 2 * (size_t)n_points * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]));
+        GROUP_CU_TRY(cudaEventRecord(g->ev1[i], g->stream[i]));
     }
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
         cudaError_t err = cudaEventSynchronize(g->ev1[i]);
         if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "group compute", err);
         float t = 0.0f;
-        cudaEventElapsedTime(&t, g->ev0[i], g->ev1[i]);
+        GROUP_CU_TRY(cudaEventElapsedTime(&t, g->ev0[i], g->ev1[i]));
         if (t > ms) ms = t;
     }
     for (int p = 0; p < n_points; ++p) {
@@ -173,19 +188,14 @@ int nmch_group_create(const nmch_params_t *params, int n_gpus, nmch_group_t **ou
     return NMCH_OK;
 }
 
-int nmch_group_init(nmch_group_t *g, unsigned long long seed)
+static int group_init_impl(nmch_group_t *g, unsigned long long seed)
 {
-    if (!g) return engine_fail(NMCH_ERR_ARG, "null group");
-    if (g->inited) return engine_fail(NMCH_ERR_STATE, "group already initialised");
-    int prev = 0;
-    cudaGetDevice(&prev);
     float ms = 0.0f;
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
-        cudaError_t err = cudaStreamCreateWithFlags(&g->stream[i], cudaStreamNonBlocking);
-        if (err == cudaSuccess) err = cudaEventCreate(&g->ev0[i]);
-        if (err == cudaSuccess) err = cudaEventCreate(&g->ev1[i]);
-        if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "group stream/event creation", err);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+        GROUP_CU_TRY(cudaStreamCreateWithFlags(&g->stream[i], cudaStreamNonBlocking));
+        GROUP_CU_TRY(cudaEventCreate(&g->ev0[i]));
+        GROUP_CU_TRY(cudaEventCreate(&g->ev1[i]));
         int rc = nmch_engine_init(g->eng[i], seed);
         if (rc) return rc;
         const float t = nmch_engine_init_ms(g->eng[i]);
@@ -202,20 +212,34 @@ int nmch_group_init(nmch_group_t *g, unsigned long long seed)
     int rc = ensure_moments(g, 1);
     if (rc == NMCH_OK && g->n > 1) {
         // first collective on a communicator sets up its channels (~100 ms): pay that here, not in compute()
-        ncclResult_t r = g_nccl.GroupStart();
-        for (int i = 0; i < g->n && r == ncclSuccess; ++i) {
-            cudaSetDevice(g->dev[i]);
-            cudaMemsetAsync(g->d_mom[i], 0, 2 * sizeof(double), g->stream[i]);
-            r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], 2, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
+        for (int i = 0; i < g->n; ++i) {
+            GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+            GROUP_CU_TRY(cudaMemsetAsync(g->d_mom[i], 0, 2 * sizeof(double), g->stream[i]));
         }
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int i = 0; i < g->n && r == ncclSuccess; ++i)
+            r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], 2, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
         if (r == ncclSuccess) r = g_nccl.GroupEnd();
         if (r != ncclSuccess) return nccl_fail("NCCL warm-up allreduce", r);
         for (int i = 0; i < g->n; ++i) {
-            cudaSetDevice(g->dev[i]);
-            cudaStreamSynchronize(g->stream[i]);
+            GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+            GROUP_CU_TRY(cudaStreamSynchronize(g->stream[i]));
         }
     }
-    cudaSetDevice(prev);
+    return rc;
+}
+
+int nmch_group_init(nmch_group_t *g, unsigned long long seed)
+{
+    if (!g) return engine_fail(NMCH_ERR_ARG, "null group");
+    if (g->inited) return engine_fail(NMCH_ERR_STATE, "group already initialised");
+    DeviceRestore restore;
+    const int rc = group_init_impl(g, seed);
+    if (rc != NMCH_OK) {
+        const std::string why = nmch_last_error();      // keep the cause: the clean-up below may overwrite it
+        nmch_group_finalize(g);                         // releases whatever the failed init had created
+        engine_fail(rc, why.c_str());
+    }
     return rc;
 }
 
@@ -229,92 +253,82 @@ int nmch_group_set_params(nmch_group_t *g, float k, float theta, float sigma)
 int nmch_group_compute(nmch_group_t *g, nmch_moments_t *out)
 {
     if (!out) return engine_fail(NMCH_ERR_ARG, "null output");
-    int prev = 0;
-    cudaGetDevice(&prev);
-    const int rc = run_points(g, nullptr, nullptr, nullptr, 1, out);
-    cudaSetDevice(prev);
-    return rc;
+    DeviceRestore restore;
+    return run_points(g, nullptr, nullptr, nullptr, 1, out);
 }
 
 int nmch_group_explore(nmch_group_t *g, const float *k, const float *theta, const float *sigma, int n_points,
                        nmch_moments_t *out)
 {
     if (!k || !theta || !sigma || !out || n_points <= 0) return engine_fail(NMCH_ERR_ARG, "bad exploration arguments");
-    int prev = 0;
-    cudaGetDevice(&prev);
-    const int rc = run_points(g, k, theta, sigma, n_points, out);
-    cudaSetDevice(prev);
-    return rc;
+    DeviceRestore restore;
+    return run_points(g, k, theta, sigma, n_points, out);
 }
 
 int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_strikes, nmch_strike_moments_t *out)
 {
     if (!g || !g->inited) return engine_fail(NMCH_ERR_STATE, "group not initialised");
     if (!strikes || !out || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return engine_fail(NMCH_ERR_ARG, "bad strike arguments");
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceRestore restore;
     int rc = ensure_moments(g, 2 * (size_t)n_strikes);          // 4 doubles per strike
     if (rc) return rc;
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
-        cudaEventRecord(g->ev0[i], g->stream[i]);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+        GROUP_CU_TRY(cudaEventRecord(g->ev0[i], g->stream[i]));
         rc = nmch_engine_compute_strikes_async(g->eng[i], g->stream[i], strikes, n_strikes, g->d_mom[i]);
-        if (rc) { cudaSetDevice(prev); return rc; }
+        if (rc) return rc;
     }
     if (g->n > 1) {
         ncclResult_t r = g_nccl.GroupStart();
         for (int i = 0; i < g->n && r == ncclSuccess; ++i)
             r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], 4 * (size_t)n_strikes, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
         if (r == ncclSuccess) r = g_nccl.GroupEnd();
-        if (r != ncclSuccess) { cudaSetDevice(prev); return nccl_fail("strike allreduce", r); }
+        if (r != ncclSuccess) return nccl_fail("strike allreduce", r);
     }
     float ms = 0.0f;
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
-        if (i == 0) cudaMemcpyAsync(g->h_mom, g->d_mom[0], 4 * (size_t)n_strikes * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]);
-        cudaEventRecord(g->ev1[i], g->stream[i]);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
+        if (i == 0)
+            GROUP_CU_TRY(cudaMemcpyAsync(g->h_mom, g->d_mom[0], 4 * (size_t)n_strikes * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]));
+        GROUP_CU_TRY(cudaEventRecord(g->ev1[i], g->stream[i]));
     }
     for (int i = 0; i < g->n; ++i) {
-        cudaSetDevice(g->dev[i]);
+        GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
         cudaError_t err = cudaEventSynchronize(g->ev1[i]);
-        if (err != cudaSuccess) { cudaSetDevice(prev); return engine_fail(NMCH_ERR_CUDA, "group strikes", err); }
+        if (err != cudaSuccess) return engine_fail(NMCH_ERR_CUDA, "group strikes", err);
         float t = 0.0f;
-        cudaEventElapsedTime(&t, g->ev0[i], g->ev1[i]);
+        GROUP_CU_TRY(cudaEventElapsedTime(&t, g->ev0[i], g->ev1[i]));
         if (t > ms) ms = t;
     }
     for (int j = 0; j < n_strikes; ++j) {
         const double *m = g->h_mom + 4 * (size_t)j;
         out[j] = nmch_strike_moments_t{strikes[j], m[0], m[1], m[2], m[3], g->n_paths, ms};
     }
-    cudaSetDevice(prev);
     return NMCH_OK;
 }
 
 int nmch_group_finalize(nmch_group_t *g)
 {
     if (!g) return engine_fail(NMCH_ERR_ARG, "null group");
-    if (!g->inited) return NMCH_OK;
-    int prev = 0;
-    cudaGetDevice(&prev);
+    // Idempotent, and also the clean-up path of an init() that failed half way: every resource is released if
+    // present, whatever the lifecycle flag says (as nmch_engine_finalize does).
+    DeviceRestore restore;
     for (int i = 0; i < g->n; ++i) {
+        if (i >= (int)g->dev.size()) break;
         cudaSetDevice(g->dev[i]);
-        if (g->stream[i]) cudaStreamSynchronize(g->stream[i]);
+        if (i < (int)g->stream.size() && g->stream[i]) cudaStreamSynchronize(g->stream[i]);
         if (i < (int)g->comm.size() && g->comm[i]) g_nccl.CommDestroy(g->comm[i]);
-        nmch_engine_finalize(g->eng[i]);
-        if (g->d_mom[i]) cudaFree(g->d_mom[i]);
-        if (g->ev0[i]) cudaEventDestroy(g->ev0[i]);
-        if (g->ev1[i]) cudaEventDestroy(g->ev1[i]);
-        if (g->stream[i]) cudaStreamDestroy(g->stream[i]);
-        g->d_mom[i] = nullptr;
-        g->ev0[i] = g->ev1[i] = nullptr;
-        g->stream[i] = nullptr;
+        if (i < (int)g->eng.size() && g->eng[i]) nmch_engine_finalize(g->eng[i]);
+        if (i < (int)g->d_mom.size() && g->d_mom[i]) { cudaFree(g->d_mom[i]); g->d_mom[i] = nullptr; }
+        if (i < (int)g->ev0.size() && g->ev0[i]) { cudaEventDestroy(g->ev0[i]); g->ev0[i] = nullptr; }
+        if (i < (int)g->ev1.size() && g->ev1[i]) { cudaEventDestroy(g->ev1[i]); g->ev1[i] = nullptr; }
+        if (i < (int)g->stream.size() && g->stream[i]) { cudaStreamDestroy(g->stream[i]); g->stream[i] = nullptr; }
     }
     g->comm.clear();
     if (g->h_mom) cudaFreeHost(g->h_mom);
     g->h_mom = nullptr;
     g->mom_cap = 0;
     g->inited = false;
-    cudaSetDevice(prev);
     return NMCH_OK;
 }
 

@@ -1,6 +1,7 @@
 // kernels.cuh -- launch-parameter blocks and launcher prototypes shared by the engine and the kernels.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "device_common.cuh"
@@ -36,6 +37,9 @@ struct FeLaunch {
     int   n_points;
     int   blocks_per_point;
     int   tiles_per_block;
+    // XORWOW sweeps walked in chunks (fe_compat_kernel / fe_xorwow_fast_kernel): blockIdx.y = chunk of chunk_points
+    // consecutive points; chunk c starts c * chunk_points * 2N draws into every path's stream (skip tables)
+    int   chunk_points, n_chunks;
     float S0, v0, K;
     float rdt;                          // r*dt
     float zr, zc;                       // rho*sqrt(dt)*c0, sqrt(1-rho^2)*sqrt(dt)*c0, c0 = sqrt(2 ln 2)
@@ -74,10 +78,11 @@ cudaError_t launch_fe_philox(const FeLaunch &L, int floor_kind, int paths_per_th
 // dense-draw variant: three steps per Philox block (NMCH_RNG_PHILOX_DENSE); block size 128, P in {1, 2, 4}
 cudaError_t launch_fe_dense(const FeLaunch &L, int floor_kind, int paths_per_thread, const FePoint *d_pts, ReduceBuffers rb,
                             float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
-cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs,
+// skip: device tables A^(q 4^m) with A = T^(2N * chunk_points) (xorwow_offset_tables_host), or nullptr when n_chunks == 1
+cudaError_t launch_fe_compat(const FeLaunch &L, int floor_kind, const RawPoint *d_pts, XorwowState xs, const uint32_t *skip,
                              ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 // XORWOW integer stream + the native fast-math step (NMCH_RNG_XORWOW_FAST); d_pts holds folded FePoint records
-cudaError_t launch_fe_xorwow_fast(const FeLaunch &L, int floor_kind, const FePoint *d_pts, XorwowState xs,
+cudaError_t launch_fe_xorwow_fast(const FeLaunch &L, int floor_kind, const FePoint *d_pts, XorwowState xs, const uint32_t *skip,
                                   ReduceBuffers rb, float *S_out, float *V_out, cudaStream_t stream, KernelInfo *info);
 
 // strike_kernels.cu: per-strike payoff / delta sums from terminal prices kept on the device
@@ -89,6 +94,8 @@ int strike_blocks_per_slot();
 struct XorwowSkipTables;                // device tables M_m^q, q = 1..3, m = 0..31
 cudaError_t xorwow_tables_create(XorwowSkipTables **out);
 void        xorwow_tables_destroy(XorwowSkipTables *t);
+// host side of the offset skip: tables of T^(draws * q * 4^m), q = 1..3, m < n_digits (device layout)
+std::vector<uint32_t> xorwow_offset_tables_host(unsigned long long draws, int n_digits);
 cudaError_t launch_xorwow_init(const XorwowSkipTables *t, unsigned long long seed,
                                unsigned long long first_path, unsigned long long n_local, XorwowState xs,
                                cudaStream_t stream);

@@ -41,6 +41,7 @@ qe_kernel(const __grid_constant__ QeLaunch L, const QePoint *__restrict__ pts, R
           float *__restrict__ S_out, float *__restrict__ V_out)
 {
     const int point = blockIdx.y;
+    NMCHB_ASSERT(point < L.n_points && (int)blockIdx.x < L.blocks_per_point);
     const QePoint pc = (pts != nullptr) ? pts[point] : L.pt0;
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < L.n_local;

@@ -11,13 +11,14 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "xorwow_device.cuh"
 
 namespace nmchb {
 
 namespace {
 
 constexpr int kDigits = 32;            // 64-bit subsequence, 2 bits per digit
-constexpr int kRowWords = 8;           // 5 state words padded to 32 bytes: two 16-byte loads per row
+constexpr int kRowWords = kXorwowRowWords;   // 5 state words padded to 32 bytes: two 16-byte loads per row
 
 struct Gf2Mat {
     uint32_t row[160][5];              // row b = image of unit vector e_b
@@ -57,6 +58,56 @@ void host_matmul(const Gf2Mat &A, const Gf2Mat &B, Gf2Mat &out)   // out = A*B (
 struct XorwowSkipTables {
     uint32_t *d_tables = nullptr;      // [kDigits][3][160][kRowWords]
 };
+
+static const Gf2Mat &one_step_matrix()
+{
+    static Gf2Mat T;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int b = 0; b < 160; ++b) {
+            uint32_t e[5] = {0, 0, 0, 0, 0};
+            e[b >> 5] = 1u << (b & 31);
+            host_step(e);
+            std::memcpy(T.row[b], e, sizeof e);
+        }
+    });
+    return T;
+}
+
+// Offset skip-ahead (what cuRAND's curand_init does for its `offset` argument with its own tables,
+// curand_kernel.h:703-719): A = T^draws by square-and-multiply
+// from the one-step matrix, then A^(q 4^m) for q = 1..3, m < n_digits, in the device table layout.  The FE kernels use
+// it to start chunk c of a sweep c * draws positions into each path's stream (fe_kernels.cu).
+std::vector<uint32_t> xorwow_offset_tables_host(unsigned long long draws, int n_digits)
+{
+    Gf2Mat acc, sq = one_step_matrix();
+    bool have = false;
+    for (unsigned long long e = draws; e != 0ull; e >>= 1) {
+        if (e & 1ull) {
+            if (have) host_matmul(acc, sq, acc);
+            else { acc = sq; have = true; }
+        }
+        if (e >> 1) host_matmul(sq, sq, sq);
+    }
+    if (!have)                                                   // draws == 0: identity
+        for (int b = 0; b < 160; ++b) {
+            std::memset(acc.row[b], 0, sizeof acc.row[b]);
+            acc.row[b][b >> 5] = 1u << (b & 31);
+        }
+    std::vector<uint32_t> host((size_t)n_digits * 3 * 160 * kRowWords, 0u);
+    Gf2Mat cur = acc;
+    for (int m = 0; m < n_digits; ++m) {
+        Gf2Mat p2, p3;
+        host_matmul(cur, cur, p2);
+        host_matmul(p2, cur, p3);
+        const Gf2Mat *pw[3] = {&cur, &p2, &p3};
+        for (int q = 0; q < 3; ++q)
+            for (int b = 0; b < 160; ++b)
+                std::memcpy(&host[(((size_t)m * 3 + q) * 160 + b) * kRowWords], pw[q]->row[b], 5 * sizeof(uint32_t));
+        if (m + 1 < n_digits) host_matmul(p2, p2, cur);              // next digit: fourth power
+    }
+    return host;
+}
 
 static const std::vector<uint32_t> &host_tables()
 {
@@ -129,25 +180,6 @@ __device__ __forceinline__ void warp_vecmat(uint32_t v[5], const uint32_t *__res
     }
 }
 
-// v <- v * M for a state private to the thread (every lane its own state, and possibly its own matrix).
-__device__ __forceinline__ void thread_vecmat(uint32_t v[5], const uint32_t *__restrict__ M)
-{
-    const uint4 *rows = reinterpret_cast<const uint4 *>(M);
-    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-#pragma unroll
-    for (int w = 0; w < 5; ++w) {
-        const uint32_t word = v[w];
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            const uint4 a = __ldg(rows + 2 * (w * 32 + j));
-            const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t *>(rows + 2 * (w * 32 + j) + 1));
-            const uint32_t mask = 0u - ((word >> j) & 1u);
-            r0 ^= a.x & mask; r1 ^= a.y & mask; r2 ^= a.z & mask; r3 ^= a.w & mask; r4 ^= b4 & mask;
-        }
-    }
-    v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3; v[4] = r4;
-}
-
 // Block of 256 consecutive paths.  When the block's first path is a multiple of 256 all its paths share the
 // digits above bit 8 of the subsequence: warp 0 applies those once for the whole block (cooperative products),
 // and every thread then applies only its own four low digits -- about a third of the work of a full walk.
@@ -174,6 +206,7 @@ xorwow_init_kernel(const uint32_t *__restrict__ tables, unsigned long long seed,
             unsigned long long hi = block_first >> 8;
             for (int mm = 4; hi != 0ull; ++mm, hi >>= 2) {
                 const unsigned q = (unsigned)(hi & 3ull);
+                NMCHB_ASSERT(mm < kDigits);
                 if (q != 0u) warp_vecmat(v, tables + ((size_t)mm * 3 + (q - 1)) * 160 * kRowWords, threadIdx.x);
             }
             if (threadIdx.x < 5) s_base[threadIdx.x] = v[threadIdx.x];
@@ -186,6 +219,7 @@ xorwow_init_kernel(const uint32_t *__restrict__ tables, unsigned long long seed,
     if (idx >= n_local) return;
     for (; sub != 0ull; ++m, sub >>= 2) {
         const unsigned q = (unsigned)(sub & 3ull);
+        NMCHB_ASSERT(m < kDigits);
         if (q != 0u) thread_vecmat(v, tables + ((size_t)m * 3 + (q - 1)) * 160 * kRowWords);
     }
     xs.d[idx] = d;

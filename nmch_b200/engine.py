@@ -119,6 +119,10 @@ class Engine:
         return [{"strike": m.strike, "moments": Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms),
                  "delta": m.sum_delta / m.n_paths, "itm": m.sum_itm / m.n_paths} for m in out]
 
+    def check(self) -> None:
+        """Synchronise and, in the checked build, sweep the guard bands / surface a failed device assert."""
+        capi.check(self._lib.nmch_engine_check(self._h))
+
     def finalize(self) -> None:
         if self._h:
             capi.check(self._lib.nmch_engine_finalize(self._h))

@@ -36,6 +36,7 @@ class NMCH:
     """Abstract base (NMCH.hpp:28-115): parameter bag + result fields."""
     _method = _eng.METHOD_FE
     _title = ""
+    _k1_kernel = False      # True for the classes that launch FE_k1 / EM_k1 in the reference (K1_MM, K1_PgM, K1_PiM)
 
     def __init__(self, NTPB, NB, T, S_0, v_0, r, k, rho, theta, sigma, N, rnd_state=PHILOX, *, compat=False,
                  dense=False, fast=False, floor="abs", device=-1, first_path=0, n_local=0, n_paths=0,
@@ -63,6 +64,12 @@ class NMCH:
                                    device=device, n_paths=n_paths, first_path=first_path, n_local=n_local,
                                    paths_per_thread=paths_per_thread)
         self.last_moments = None
+        self.legacy_k1_moment = False
+
+    def set_legacy_k1_moment(self, on: bool) -> None:
+        """Exact legacy output of the reference's K1 kernels: price_squared = E[X^2]/n^2 (NMCH_FE.cu:56-58,
+        NMCH_EM.cu:129-131: they reduce (payoff/n)^2/n).  K1 classes only; K2 / K3 are unaffected."""
+        self.legacy_k1_moment = bool(on)
 
     # lifecycle -------------------------------------------------------------------------------
     def init(self, seed: int) -> None:
@@ -75,6 +82,9 @@ class NMCH:
         self.last_moments = m
         self.strike_price = float(np.float32(m.mean))
         self.price_squared = float(np.float32(m.mean_sq))
+        if self.legacy_k1_moment and self._k1_kernel:
+            n = float(self.state_numbers)
+            self.price_squared = float(np.float32(m.sum_payoff_sq / n / n / n))
         self.Tim_exec = m.exec_ms
 
     def finalize(self) -> None:
@@ -129,15 +139,17 @@ class NMCH_FE_K1(NMCH):
     _title = "FORWARD-EULER"
 
 
-class NMCH_FE_K1_MM(NMCH_FE_K1): pass
-class NMCH_FE_K2_MM(NMCH_FE_K1_MM): pass
+class NMCH_FE_K1_MM(NMCH_FE_K1): _k1_kernel = True
+class NMCH_FE_K2_MM(NMCH_FE_K1_MM): _k1_kernel = False
 class NMCH_FE_K3_MM(NMCH_FE_K2_MM): pass
-class NMCH_FE_K1_PgM(NMCH_FE_K1): pass
-class NMCH_FE_K1_PiM(NMCH_FE_K1): pass
+class NMCH_FE_K1_PgM(NMCH_FE_K1): _k1_kernel = True
+class NMCH_FE_K1_PiM(NMCH_FE_K1): _k1_kernel = True
 
 
 class NMCH_FE_K2_PHILOX_MM(NMCH_FE_K1_MM):
     """Non-template in the reference (NMCH_FE.hpp:142): always the Philox tag."""
+
+    _k1_kernel = False
 
     def __init__(self, NTPB, NB, T, S_0, v_0, r, k, rho, theta, sigma, N, **kw):
         super().__init__(NTPB, NB, T, S_0, v_0, r, k, rho, theta, sigma, N, PHILOX, **kw)
@@ -148,8 +160,8 @@ class NMCH_EM_K1(NMCH):
     _title = "EXACT-METHOD"
 
 
-class NMCH_EM_K1_MM(NMCH_EM_K1): pass
-class NMCH_EM_K2_MM(NMCH_EM_K1_MM): pass
+class NMCH_EM_K1_MM(NMCH_EM_K1): _k1_kernel = True
+class NMCH_EM_K2_MM(NMCH_EM_K1_MM): _k1_kernel = False
 class NMCH_EM_K3_MM(NMCH_EM_K2_MM): pass
 
 

@@ -936,6 +936,26 @@ int orc_exploration_grid(int steps, int apply_filter, float *k_out, float *theta
     return n;
 }
 
+/* Generator initialisation alone for paths [first_path, first_path + n_paths): what the reference's init_curand_state_k
+ * does (random.cu:6-10) and reports as Tim_init, outside Tim_exec.  bench.py times this next to orc_fe_run / orc_em_run
+ * (which initialise inside their path loop) so that the CPU baseline can be quoted on the same span as the GPU arm.
+ * Returns a checksum of the states so that the work cannot be optimised away. */
+uint64_t orc_rng_init_only(int rng_kind, uint64_t seed, uint64_t first_path, uint64_t n_paths, int threads)
+{
+    uint64_t acc = 0;
+    xorwow_build_matrices();
+    if (threads <= 0) threads = orc_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc) num_threads(threads) schedule(static)
+#endif
+    for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+        orc_rng_t st;
+        orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, 0);
+        acc += (uint64_t)orc_rng_next(&st);
+    }
+    return acc;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

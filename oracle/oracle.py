@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
         L.orc_exploration_grid.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p, C.c_int]
         L.orc_exploration_grid.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
+        L.orc_rng_init_only.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+        L.orc_rng_init_only.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -248,3 +250,17 @@ def std_error(mean: float, mean_sq: float, n: int) -> float:
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def host_threads() -> int:
+    """Host threads this process may run on (its CPU affinity), whatever OMP_NUM_THREADS says: torch.distributed.run
+    exports OMP_NUM_THREADS=1, which would make omp_get_max_threads() -- and a CPU baseline sized by it -- one thread."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def rng_init_only(rng=RNG_XORWOW, seed=1234, first_path=0, n_paths=1024, threads=0) -> int:
+    """curand_init for every path and nothing else (the reference's Tim_init span); returns a checksum."""
+    return lib().orc_rng_init_only(rng, seed, first_path, n_paths, threads)

@@ -8,7 +8,8 @@
  * Everything numerical below is the reference's code: this file only parses flags, calls
  * init/compute through the public API and prints what the getters return.
  *
- *   nmch_ref_harness --method fe|em --rng xorwow|philox|mrg [--kernel k2|k3] --NTPB .. --NB .. --N ..
+ *   nmch_ref_harness --method fe|em --rng xorwow|philox|mrg [--kernel k1|k2|k3] --NTPB .. --NB .. --N ..
+ *                    (k1 = NMCH_*_K1_MM: needs a power-of-two NTPB, stores E[X^2]/n^2 in price_squared)
  *                    [--k --theta --sigma --rho --T --S_0 --v_0 --r --seed] [--repeat R]
  *                    [--points FILE]   (lines "k theta sigma": one set_* + compute() per line)
  * One JSON object per compute() on stdout.
@@ -96,6 +97,8 @@ int main(int argc, char **argv)
     }
     const bool x = a.rng == "xorwow";
     if (a.rng == "mrg") {
+        if (a.method == "fe" && a.kernel == "k1") return run<NMCH_FE_K1_MM<curandStateMRG32k3a_t>>(a);
+        if (a.method == "em" && a.kernel == "k1") return run<NMCH_EM_K1_MM<curandStateMRG32k3a_t>>(a);
         if (a.method == "fe" && a.kernel == "k2") return run<NMCH_FE_K2_MM<curandStateMRG32k3a_t>>(a);
         if (a.method == "fe" && a.kernel == "k3") return run<NMCH_FE_K3_MM<curandStateMRG32k3a_t>>(a);
         if (a.method == "em" && a.kernel == "k2") return run<NMCH_EM_K2_MM<curandStateMRG32k3a_t>>(a);
@@ -105,10 +108,12 @@ int main(int argc, char **argv)
     }
     if (!x && a.rng != "philox") { fprintf(stderr, "unknown rng %s\n", a.rng.c_str()); return 2; }
     if (a.method == "fe") {
+        if (a.kernel == "k1") return x ? run<NMCH_FE_K1_MM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K1_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k2") return x ? run<NMCH_FE_K2_MM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K2_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k3") return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k2philox") return run<NMCH_FE_K2_PHILOX_MM>(a);
     } else if (a.method == "em") {
+        if (a.kernel == "k1") return x ? run<NMCH_EM_K1_MM<curandStateXORWOW_t>>(a) : run<NMCH_EM_K1_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k2") return x ? run<NMCH_EM_K2_MM<curandStateXORWOW_t>>(a) : run<NMCH_EM_K2_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k3") return x ? run<NMCH_EM_K3_MM<curandStateXORWOW_t>>(a) : run<NMCH_EM_K3_MM<curandStatePhilox4_32_10_t>>(a);
     }

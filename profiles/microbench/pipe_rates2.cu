@@ -272,5 +272,12 @@ int main(int argc, char **argv)
     run<WIDE, 11, LOP, 8, FFMA3, 24, MUFU_EX2, 9, LOP, 0, true>("EM trial mix with 11 WIDE (3 trials per 2 blocks)");
     run<WIDE, 9, LOP, 7, FFMA3, 24, MUFU_EX2, 9, LOP, 0, true>("EM trial mix with 9 WIDE (2 trials per block)");
     run<WIDE, 9, LOP, 7, FFMA3, 24, MUFU_EX2, 7, LOP, 0, true>("EM packed trial mix: 9 WIDE, 16 ALU, 24 FP32, 7 MUFU");
+    printf("-- round-2 EM split trial (2 trials per block, boost recycled from the accept test): SASS of em_native_kernel<kEmSplit>\n");
+    run<WIDE, 9, LOP, 10, FFMA3, 21, MUFU_EX2, 8, LOP, 0, true>("r02 EM split trial, boosted: 8.5 -> 9 WIDE, 19 ALU, 21 FP32, 8 MUFU");
+    run<WIDE, 9, LOP, 10, FFMA3, 18, MUFU_EX2, 7, LOP, 0, true>("r02 EM split trial, no boost: 9 WIDE, 19 ALU, 18 FP32, 7 MUFU");
+    run<WIDE, 17, LOP, 21, FFMA3, 42, MUFU_EX2, 16, LOP, 0, true>("r02 EM split, boosted, TWO trials (one Philox block): 17 WIDE, 38 ALU, 42 FP32, 16 MUFU");
+    run<WIDE, 17, LOP, 21, FFMA3, 36, MUFU_EX2, 14, LOP, 0, true>("r02 EM split, no boost, TWO trials: 17 WIDE, 38 ALU, 36 FP32, 14 MUFU");
+    run<WIDE, 9, LOP, 8, FFMA3, 21, MUFU_EX2, 8, LOP, 0, true>("... boosted with 17 ALU");
+    run<WIDE, 9, LOP, 10, FFMA3, 21, MUFU_EX2, 6, LOP, 0, true>("... boosted with 6 MUFU");
     return 0;
 }

@@ -137,6 +137,15 @@ float NMCH<rnd_state>::compute_strikes(int n_strikes, const float *strikes, floa
 }
 
 template <typename rnd_state>
+void NMCH<rnd_state>::apply_legacy_k1_moment()
+{
+    // reference FE_k1 / EM_k1: SR = payoff / n; VR = SR * SR / n; price_squared = sum VR = (sum payoff^2) / n^3
+    if (!legacy_k1_moment) return;
+    const double n = (double)path_count();
+    price_squared = (float)(sum_payoff_sq / n / n / n);
+}
+
+template <typename rnd_state>
 void NMCH<rnd_state>::engine_finalize()
 {
     if (group) testNMCH(nmch_group_finalize(group));               // idempotent, unlike the reference's double free

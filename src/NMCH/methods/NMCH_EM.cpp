@@ -43,7 +43,7 @@ NMCH_EM_CTOR(NMCH_EM_K2_MM, NMCH_EM_K1_MM)
 NMCH_EM_CTOR(NMCH_EM_K3_MM, NMCH_EM_K2_MM)
 
 template <typename S> void NMCH_EM_K1_MM<S>::init(unsigned long long seed) { this->run_init(seed); }
-template <typename S> void NMCH_EM_K1_MM<S>::compute() { this->run_compute(); }
+template <typename S> void NMCH_EM_K1_MM<S>::compute() { this->run_compute(); this->apply_legacy_k1_moment(); }   // EM_k1, NMCH_EM.cu:129-131
 template <typename S> void NMCH_EM_K2_MM<S>::compute() { this->run_compute(); }
 template <typename S> void NMCH_EM_K3_MM<S>::compute() { this->run_compute(); }
 

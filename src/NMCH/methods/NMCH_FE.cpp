@@ -49,13 +49,14 @@ NMCH_FE_CTOR(NMCH_FE_K1_PgM, NMCH_FE_K1)
 NMCH_FE_CTOR(NMCH_FE_K1_PiM, NMCH_FE_K1)
 
 template <typename S> void NMCH_FE_K1_MM<S>::init(unsigned long long seed) { this->run_init(seed); }
-template <typename S> void NMCH_FE_K1_MM<S>::compute() { this->run_compute(); }
+// the three classes below launch FE_k1 in the reference (NMCH_FE.cu:516-546, 556-612, 622-689): the K1 moment quirk is theirs
+template <typename S> void NMCH_FE_K1_MM<S>::compute() { this->run_compute(); this->apply_legacy_k1_moment(); }
 template <typename S> void NMCH_FE_K2_MM<S>::compute() { this->run_compute(); }
 template <typename S> void NMCH_FE_K3_MM<S>::compute() { this->run_compute(); }
 template <typename S> void NMCH_FE_K1_PgM<S>::init(unsigned long long seed) { this->run_init(seed); }
-template <typename S> void NMCH_FE_K1_PgM<S>::compute() { this->run_compute(); }
+template <typename S> void NMCH_FE_K1_PgM<S>::compute() { this->run_compute(); this->apply_legacy_k1_moment(); }
 template <typename S> void NMCH_FE_K1_PiM<S>::init(unsigned long long seed) { this->run_init(seed); }
-template <typename S> void NMCH_FE_K1_PiM<S>::compute() { this->run_compute(); }
+template <typename S> void NMCH_FE_K1_PiM<S>::compute() { this->run_compute(); this->apply_legacy_k1_moment(); }
 template <typename S> void NMCH_FE_K1_PiM<S>::finalize() { NMCH_FE_K1<S>::finalize(); }
 
 NMCH_FE_K2_PHILOX_MM::NMCH_FE_K2_PHILOX_MM(int NTPB, int NB, float T, float S_0, float v_0, float r, float k, float rho,

@@ -4,6 +4,8 @@
 //   --rng philox|xorwow|philox-compat|philox-dense|xorwow-fast   generator tag / stream mode (reference CLI: Philox, nmch.cu:119,130)
 //   --gpus N            shard the paths over N GPUs, one NCCL allreduce of the moments
 //   --paths-per-thread P, --json (one machine-readable line after the report)
+//   --legacy-k1         run the K1 class of the method (the reference CLI runs K3) with its E[X^2]/n^2 moment quirk
+//                       (reference NMCH_FE.cu:56-58, NMCH_EM.cu:129-131), for exact legacy output
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,7 +26,7 @@ struct Options {
     float T = 1.0f, S_0 = 1.0f, v_0 = 0.1f, r = 0.0f, k = 0.5f, rho = -0.7, theta = 0.1f, sigma = 0.3f;
     unsigned long long seed = 1234;
     std::string method = "fe", g = "abs", rng = "philox", strikes;
-    bool json = false;
+    bool json = false, legacy_k1 = false;
 };
 
 void usage(const char *argv0)
@@ -54,6 +56,7 @@ void usage(const char *argv0)
     printf("  --gpus <int>       GPUs to shard the paths over (default: 1)\n");
     printf("  --paths-per-thread <int>  1, 2, 4 or 8 (default: auto)\n");
     printf("  --strikes <k1,k2,..>  Also price these strikes (and pathwise deltas) on a second pass of the streams\n");
+    printf("  --legacy-k1        Run the method's K1 class with the reference's K1 moment quirk (E[X^2] field = E[X^2]/n^2)\n");
     printf("  --json             Also print one JSON line with the raw moments\n");
 }
 
@@ -67,17 +70,23 @@ int run(const Options &o)
     m.set_philox_dense(o.rng == "philox-dense");
     m.set_xorwow_fast(o.rng == "xorwow-fast");
     m.set_paths_per_thread(o.ppt);
+    m.set_legacy_k1_moment(o.legacy_k1);
     m.init(o.seed);
     m.compute();
     m.print_stats();
     if (o.json) {
         const double n = (double)o.NTPB * (double)o.NB;
         const double units = o.method == "em" ? n : n * o.N;
+        // the reference's err formula is NaN when price_squared carries the K1 quirk (n E[X^2]/n^2 - E[X]^2 < 0): JSON has no NaN
+        char err_txt[32];
+        const float err = m.get_err();
+        if (err == err) snprintf(err_txt, sizeof err_txt, "%.9g", err);
+        else snprintf(err_txt, sizeof err_txt, "null");
         printf("{\"method\": \"%s\", \"rng\": \"%s\", \"floor\": \"%s\", \"gpus\": %d, \"n_paths\": %.0f, \"N\": %d, "
                "\"sum_payoff\": %.17g, \"sum_payoff_sq\": %.17g, \"E\": %.9g, \"E2\": %.9g, \"std_error\": %.6g, "
-               "\"err\": %.9g, \"exec_ms\": %.6f, \"%s\": %.6g}\n",
+               "\"err\": %s, \"exec_ms\": %.6f, \"%s\": %.6g}\n",
                o.method.c_str(), o.rng.c_str(), o.g.c_str(), o.gpus, n, o.N, m.get_sum_payoff(), m.get_sum_payoff_sq(),
-               m.get_strike_price(), m.get_price_squared(), m.get_std_error(), m.get_err(), m.get_execution_time(),
+               m.get_strike_price(), m.get_price_squared(), m.get_std_error(), err_txt, m.get_execution_time(),
                o.method == "em" ? "paths_per_s" : "path_steps_per_s", units / (m.get_execution_time() * 1e-3));
     }
     if (!o.strikes.empty()) {
@@ -123,6 +132,7 @@ int main(int argc, char **argv)
         else if (has("--paths-per-thread")) o.ppt = atoi(argv[++i]);
         else if (has("--strikes")) o.strikes = argv[++i];
         else if (strcmp(argv[i], "--json") == 0) o.json = true;
+        else if (strcmp(argv[i], "--legacy-k1") == 0) o.legacy_k1 = true;
         else if (strcmp(argv[i], "--help") == 0) { usage(argv[0]); return 0; }
     }
     if (o.rng != "philox" && o.rng != "xorwow" && o.rng != "philox-compat" && o.rng != "philox-dense" &&
@@ -135,6 +145,10 @@ int main(int argc, char **argv)
         return 1;
     }
     const bool x = o.rng == "xorwow" || o.rng == "xorwow-fast";
+    if (o.legacy_k1 && o.method == "fe")
+        return x ? run<NMCH_FE_K1_MM<curandStateXORWOW_t>>(o) : run<NMCH_FE_K1_MM<curandStatePhilox4_32_10_t>>(o);
+    if (o.legacy_k1 && o.method == "em")
+        return x ? run<NMCH_EM_K1_MM<curandStateXORWOW_t>>(o) : run<NMCH_EM_K1_MM<curandStatePhilox4_32_10_t>>(o);
     if (o.method == "fe")
         return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(o) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(o);
     if (o.method == "em")

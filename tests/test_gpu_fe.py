@@ -238,6 +238,37 @@ def test_explore_equals_sequential_computes(rng):
         assert b.sum_payoff == s.sum_payoff and b.sum_payoff_sq == s.sum_payoff_sq
 
 
+@pytest.mark.parametrize("rng", [1, 5])
+@pytest.mark.parametrize("n,n_points,N", [(5120, 200, 20), (5120 + 77, 37, 33), (1 << 16, 9, 10), (256, 1000, 4)])
+def test_xorwow_sweep_in_chunks_equals_the_in_thread_walk(rng, n, n_points, N):
+    """XORWOW sweeps (compat and fast) cut the point walk into chunks of consecutive points when the paths cannot fill
+    the GPU (the reference's own exploration is 5120 paths x 200 points, exploration.cu:24-25); chunk c starts
+    c * chunk_points * 2N draws down each path's stream through the offset skip-ahead.  Same draws per (path, point),
+    same blocks per point: the sums are BIT-identical to sequential compute() calls, and the streams continue
+    from the same place afterwards."""
+    rs = np.random.default_rng(n_points)
+    k = rs.uniform(0.1, 5.0, n_points).astype(np.float32)
+    th = rs.uniform(0.01, 0.5, n_points).astype(np.float32)
+    sg = rs.uniform(0.1, 1.0, n_points).astype(np.float32)
+    with E.Engine(NTPB=1, NB=1, N=N, rng=rng, n_paths=n) as e:
+        e.init(77)
+        batched = e.explore(k, th, sg)
+        info = e.launch_info()
+        after = e.compute()                                # continues after the sweep
+    assert info["grid_y"] > 1 or n >= 148 * 1536, info   # the chunked path is the one under test
+    with E.Engine(NTPB=1, NB=1, N=N, rng=rng, n_paths=n) as e:
+        e.init(77)
+        seq = []
+        for i in range(n_points):
+            e.set_params(float(k[i]), float(th[i]), float(sg[i]))
+            seq.append(e.compute())
+        e.set_params(0.5, 0.1, 0.3)
+        after_seq = e.compute()
+    for i, (b, s_) in enumerate(zip(batched, seq)):
+        assert b.sum_payoff == s_.sum_payoff and b.sum_payoff_sq == s_.sum_payoff_sq, i
+    assert after.sum_payoff == after_seq.sum_payoff and after.sum_payoff_sq == after_seq.sum_payoff_sq
+
+
 def test_explore_compat_matches_oracle_sweep():
     k, th, sg = o.exploration_grid(5, apply_filter=True)
     k, th, sg = k[:6], th[:6], sg[:6]
@@ -337,7 +368,7 @@ def test_failed_init_cleans_up_and_reports_cause():
     e = E.Engine(NTPB=1, NB=1, N=10, rng=1, n_paths=1 << 40)       # 26 TB of XORWOW state: cudaMalloc must fail
     with pytest.raises(capi.NmchError) as ei:
         e.init(1)
-    assert ei.value.status == capi.ERR_CUDA and "cudaMalloc" in str(ei.value)
+    assert ei.value.status == capi.ERR_CUDA and "xorwow states" in str(ei.value) and "cudaErrorMemoryAllocation" in str(ei.value)
     with pytest.raises(capi.NmchError):
         e.compute()
     e.finalize()
