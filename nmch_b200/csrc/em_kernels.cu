@@ -48,6 +48,8 @@ struct EmPoint {
     float f_t1;         // c0 * sqrt(c/2)          V' = (f_t1 z' + sqrt(f_ev V))^2 + f_g2s v [boost]
     float f_ev;         // lc * c = e^{-k dt}
     float f_scale;      // c / 2                   (Poisson-mixture path)
+    float f_hs;         // f_h / f_c^2             log test on the SCALED proposal xs = f_c x'
+    float f_lg2s;       // log2(f_g2s)             boosted gamma term assembled in the log2 domain
     float k, ktheta_T, inv_sigma;
     int   kind;         // kEmSplit (boosted gamma, 1/2 < d < 3/2), kEmSplitPacked (d >= 3/2) or kEmMixture (d <= 1/2)
     int   index;        // position of the point in the caller's list (stream id, result slot): launches group points by kind
@@ -75,58 +77,67 @@ __device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, float 
     n2 = r * cos_approx(ang);
 }
 
-// One Marsaglia-Tsang trial for Gamma(shape >= 1) given x ~ N(0,1), u ~ U(0,1).  Returns accept; g = d*v^3.
-__device__ __forceinline__ bool mt_trial(float x, float u, float mt_d, float mt_c, float &g)
-{
-    const float v1 = fmaf(mt_c, x, 1.0f);
-    const float v = v1 * v1 * v1;
-    const float x2 = x * x;
-    g = mt_d * v;
-    if (v1 <= 0.0f) return false;
-    if (u < fmaf(-0.0331f * x2, x2, 1.0f)) return true;                          // squeeze
-    return __logf(u) < fmaf(0.5f, x2, mt_d * (1.0f - v + __logf(v)));
-}
+// log2(k!) for k < 10; copied to shared memory by the kernels that sample Poisson counts (a per-lane index into
+// constant memory would serialise)
+__constant__ float kLg2Factorial[10] = {0.0f, 0.0f, 1.0f, 2.5849625f, 4.5849625f, 6.9068906f,
+                                        9.4918531f, 12.2992080f, 15.2992080f, 18.4691330f};
 
-__constant__ float kLnFactorial[10] = {0.0f, 0.0f, 0.69314718f, 1.79175947f, 3.17805383f, 4.78749174f,
-                                       6.57925121f, 8.52516136f, 10.6046029f, 12.8018275f};
-__device__ __forceinline__ float ln_factorial_small(int k) { return kLnFactorial[k]; }
-
-// log of the Poisson pmf, FP32-stable for large mu (the textbook  -mu + k ln mu - lgamma(k+1)  cancels badly)
-__device__ __forceinline__ float poisson_log_pmf(float k, float mu)
+// One Hoermann-PTRS trial for Poisson(mu), mu >= 10, from two uniforms.  Returns accept, result in k.
+// Branch-free: the algorithm's quick-acceptance squeeze is dropped (it only short-cuts trials the exact test accepts),
+// and the exact test   ln(v inv_alpha / (a / us^2 + b)) <= -mu + k ln mu - ln k!   is evaluated in the log2 domain with
+// single-instruction transcendentals, arranged so that none of them amplifies its 2^-22 absolute error:
+//   k >= 10:  ln k! by Stirling (three terms: 1e-8 at k = 10), so the right side is
+//               k (ln(1 - delta) + delta) - ln(2 pi k)/2 - 1/(12k) + 1/(360k^3),     delta = (k - mu) / k
+//             ln(1 - delta) + delta = -delta s - 2 s^3 (1/3 + s^2/5 + s^4/7 + s^6/9 + s^8/11),  s = delta / (2 - delta)
+//             (the atanh series; no cancellation; used while |s| < 0.3, i.e. |delta| < 0.46 -- beyond that the plain
+//             lg2(mu / k) is far from zero and accurate enough).  ln(2 pi k)/2 rides in the left side's logarithm.
+//   k < 10:   -mu + k ln mu - ln k! directly (table), values of order 10.
+__device__ __forceinline__ bool ptrs_trial(float mu, float u_raw, float v, const float *__restrict__ lg2fact, float &k)
 {
-    if (k < 10.0f) return -mu + k * logf(mu) - ln_factorial_small((int)k);
-    const float r = mu / k;
-    const float ik = 1.0f / k;
-    const float stirling = fmaf(ik * ik * ik, 1.0f / 360.0f, -ik * (1.0f / 12.0f));
-    return k * (logf(r) + (1.0f - r)) - 0.5f * logf(6.28318531f * k) + stirling;
-}
-
-// One Hoermann-PTRS trial (mu >= 10).  Returns accept, result in k.
-__device__ __forceinline__ bool ptrs_trial(float mu, float u_raw, float v, float &k)
-{
+    constexpr float kLn2 = 0.69314718f, kLog2e = 1.44269504f;
     const float smu = sqrt_approx(mu);
     const float b = fmaf(2.53f, smu, 0.931f);
     const float a = fmaf(0.02483f, b, -0.059f);
     // the hat's constants may be approximate (MUFU.RCP, 1e-7): they only shape the proposal and enter the exact test
-    // below consistently; the target pmf itself is evaluated with IEEE division and logf
+    // below consistently
     const float inv_alpha = fmaf(1.1328f, rcp_approx(b - 3.4f), 1.1239f);
-    const float vr = fmaf(-3.6224f, rcp_approx(b - 2.0f), 0.9277f);
     const float u = u_raw - 0.5f;
     const float us = 0.5f - fabsf(u);
     const float inv_us = rcp_approx(us);
     k = floorf(fmaf(fmaf(2.0f * a, inv_us, b), u, mu + 0.43f));
-    if (us >= 0.07f && v <= vr) return true;
-    if (k < 0.0f || (us < 0.013f && v > us)) return false;
-    return logf(v * inv_alpha * rcp_approx(fmaf(a * inv_us, inv_us, b))) <= poisson_log_pmf(k, mu);
+    const bool big = k >= 10.0f;
+    const float t = v * inv_alpha * rcp_approx(fmaf(a * inv_us, inv_us, b));
+    // left side (log2): lg2(t), plus lg2(2 pi k)/2 when Stirling is used: one logarithm of t^2 * 2 pi k, halved
+    const float lhs = 0.5f * lg2_approx(big ? (t * t) * (6.28318531f * k) : t * t);
+    const float ik = rcp_approx(big ? k : 1.0f);
+    const float delta = (k - mu) * ik;
+    const float sv = delta * rcp_approx(2.0f - delta);
+    const float s2 = sv * sv;
+    float poly = fmaf(s2, 1.0f / 11.0f, 1.0f / 9.0f);
+    poly = fmaf(poly, s2, 1.0f / 7.0f);
+    poly = fmaf(poly, s2, 1.0f / 5.0f);
+    poly = fmaf(poly, s2, 1.0f / 3.0f);
+    const float f_series = -fmaf(2.0f * sv * s2, poly, delta * sv);           // ln(1 - delta) + delta
+    const bool near = fabsf(sv) < 0.3f;
+    // one more logarithm serves both remaining cases: lg2(mu / k) (k >= 10, far from mu) or lg2(mu) (k < 10)
+    const float lgx = lg2_approx(big ? mu * ik : mu);
+    const float f_log = fmaf(lgx, kLn2, delta);                               // ln(mu/k) + 1 - mu/k
+    const float ik2 = ik * ik;
+    const float stirling = ik * fmaf(ik2, 1.0f / 360.0f, -1.0f / 12.0f);      // -1/(12k) + 1/(360k^3)
+    const float rhs_big = fmaf(k, near ? f_series : f_log, stirling) * kLog2e;
+    const int ki = big ? 0 : max((int)k, 0);
+    const float rhs_small = fmaf(k, lgx, -fmaf(mu, kLog2e, lg2fact[ki]));
+    const float rhs = big ? rhs_big : rhs_small;
+    return (k >= 0.0f) && !(us < 0.013f && v > us) && (lhs <= rhs);
 }
 
 // Poisson by inversion (mu < 10): exact, one uniform.
 __device__ __forceinline__ float poisson_inversion(float mu, float u)
 {
-    float p = __expf(-mu), cdf = p, k = 0.0f;
+    float p = ex2_approx(-1.44269504f * mu), cdf = p, k = 0.0f;
     while (u > cdf && k < 80.0f) {
         k += 1.0f;
-        p *= mu / k;
+        p *= mu * rcp_approx(k);
         cdf += p;
     }
     return k;
@@ -137,7 +148,8 @@ __device__ __forceinline__ float poisson_inversion(float mu, float u)
 //   radius uniform = wa[31:9] (23 bits)    angle = wa[8:0] : wc[31:23] (18 bits; an equispaced grid of 2^18 angles keeps
 //   every trigonometric moment below that order exact)    accept-test uniform = wc[22:0] (23 bits)
 // Marsaglia-Tsang trial for Gamma(a [+1]) with x = c0 xp, v = (1 + c x)^3: accept iff v > 0 and
-//   lg2 u < rhs = (x^2/2 + d (1 - v)) log2 e + d log2 v         (the exact test; no squeeze, hence no divergence)
+//   lg2 u < rhs = (x^2/2 + d (1 - v)) log2 e + d log2 v         (the exact test; no squeeze, hence no divergence;
+//   evaluated on the scaled proposal xs = mt_c x with f_hs = log2 e / (2 mt_c^2), so that v = (1 + xs)^3)
 // BOOST (shape a < 1): Gamma(a) = Gamma(a+1) U^(1/a) with U = 2^(lg2 u - rhs): given acceptance, rhs - lg2 u is an
 // exponential (rate ln 2) independent of the proposal -- the accept uniform's unused excess, so no extra random field
 // and one MUFU.EX2 instead of LG2 + EX2.  (Marsaglia-Tsang's acceptance ratio never exceeds one, i.e. rhs <= 0.)
@@ -149,16 +161,19 @@ __device__ __forceinline__ bool em_split_trial(uint32_t wa, uint32_t wc, const E
     // (wa << 14 | wc >> 18) masked to mantissa bits 22..5, exponent of [1, 2) -- one funnel shift, one LOP3
     const float ang = __uint_as_float(and_or(__funnelshift_r(wc, wa, 18), 0x7fffe0u, 0x3f800000u)) * 6.2831855f;
     zp = rad * sin_approx(ang);
-    const float xp = rad * cos_approx(ang);
-    const float v1 = fmaf(pc.f_c, xp, 1.0f);
+    // Every FP32 instruction below has at most ONE operand that is not a per-thread register (a point constant in a
+    // uniform register, or an immediate): an FFMA with two of them costs a register move per trial.
+    const float xs = (rad * pc.f_c) * cos_approx(ang);        // mt_c x: the proposal already scaled
+    const float v1 = xs + 1.0f;
     const float v = v1 * v1 * v1;
-    const float x2 = xp * xp;
-    float rhs = fmaf(x2, pc.f_h, fmaf(-pc.f_dl, v, pc.f_dl));
-    rhs = fmaf(pc.mt_d, lg2_approx(v), rhs);                  // v1 <= 0: lg2 gives NaN (v < 0) or -inf (v = 0), so the
+    const float lv = lg2_approx(v);                           // v1 <= 0: NaN (v < 0) or -inf (v = 0), so the comparison
+    float rhs = (xs * xs) * pc.f_hs;                          // below is false: no separate v1 > 0 test
+    rhs = fmaf(1.0f - v, pc.f_dl, rhs);
+    rhs = fmaf(lv, pc.mt_d, rhs);
     const float lu = lg2_approx(__uint_as_float(and_or(wc, 0x7fffffu, 0x3f800000u)) - 0.99999994f);
-    g2 = pc.f_g2s * v;
-    if constexpr (BOOST) g2 *= ex2_approx(pc.inv_a * (lu - rhs));
-    return lu < rhs;                                          // comparison below is false: no separate v1 > 0 test
+    if constexpr (BOOST) g2 = ex2_approx(fmaf(lu - rhs, pc.inv_a, lv + pc.f_lg2s));   // f_g2s v U^(1/a), one EX2
+    else g2 = pc.f_g2s * v;
+    return lu < rhs;
 }
 
 // Block shape of the native kernel (tuning builds may override: -DNMCHB_EM_THREADS=.. -DNMCHB_EM_MINB=..)
@@ -179,13 +194,32 @@ constexpr int kEmSplit = 0, kEmMixture = 1, kEmSplitPacked = 2, kEmAny = 3;
 // V = V_N, acc = V_1 + ... + V_N and blk = the first unused block (the terminal draw takes it).
 template <int KIND, typename NextBlock>
 __device__ __forceinline__ void em_variance_path(const EmLaunch &L, const EmPoint &pc, bool valid, NextBlock next_block,
-                                                 float &V, float &acc, uint32_t &blk)
+                                                 const float *__restrict__ lg2fact, float &V, float &acc, uint32_t &blk)
 {
     int step = valid ? 0 : L.N;                              // lanes past the end of the shard take part in the votes only
     if constexpr (KIND == kEmSplit || KIND == kEmSplitPacked) {
         // chi-square split: two trials per Philox block, four per iteration (em_split_trial).  Only the last FFMA pair
         // of a trial depends on V, so the four trials of a group overlap.  The loop is warp-uniform (vote): the block
         // counter is the same in every lane, and with it the path-independent multiplies of a block.
+        // While EVERY lane still has four steps to go, a group of four trials cannot overshoot N: no bound test per trial.
+        while (__all_sync(0xffffffffu, step + 4 <= L.N)) {
+            const U4 b0 = next_block(blk), b1 = next_block(blk + 1u);
+            blk += 2u;
+            const uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float zp, g2;
+                const bool ok = em_split_trial<KIND == kEmSplit>(w[2 * j], w[2 * j + 1], pc, zp, g2);
+                const float t = fmaf(pc.f_t1, zp, sqrt_approx(pc.f_ev * V));
+                const float Vn = fmaf(t, t, g2);
+                if (ok) {
+                    acc = __fadd_rn(acc, Vn);
+                    V = Vn;
+                    ++step;
+                }
+            }
+        }
+        // the last few steps of the warp's slowest and fastest lanes: the same group, with the bound test
         while (__any_sync(0xffffffffu, step < L.N)) {
             const U4 b0 = next_block(blk), b1 = next_block(blk + 1u);
             blk += 2u;
@@ -204,16 +238,19 @@ __device__ __forceinline__ void em_variance_path(const EmLaunch &L, const EmPoin
             }
         }
     } else {
-        // Poisson mixture (d <= 1/2): per iteration ONE Philox block feeds a Poisson trial (two 23-bit uniforms)
-        // and, from disjoint bits of the same block, one Marsaglia-Tsang trial for Gamma(d + N) (23-bit radius,
-        // 19-bit angle, 23-bit accept uniform, 17-bit boost uniform: 128 bits in all).  A lane that already holds
-        // N skips the Poisson part, so a gamma retry never re-draws (and never biases) N.
+        // Poisson mixture (d <= 1/2): per iteration ONE Philox block (x, y, z, w) feeds a Poisson trial -- uniforms from
+        // x[31:9] and y[31:9] -- and, from disjoint bits, one Marsaglia-Tsang trial for Gamma(d + N): radius z[31:9],
+        // angle z[8:0] : w[31:23], accept uniform w[22:0]; the shape < 1 boost (N = 0) is recycled from the accept test
+        // like in the split sampler.  A lane that already holds N skips the Poisson part, so a gamma retry never re-draws
+        // (and never biases) N.  The gamma trial itself is branch-free with a per-lane shape:
+        //   accept iff lg2 u < md (log2e (4.5 xs^2 + 1 - v) + lg2 v),  xs = x / sqrt(9 md),  v = (1 + xs)^3,  md = shape - 1/3.
         // Acceptance rates are >= 0.85 per trial and the host validates every folded constant (finite, positive),
         // so the loop terminates; the cap is a belt against a hang: a path that exhausts it ends early with V = NaN,
-        // which the payoff stage below carries into the sums (a NaN result, not a silently dropped path).
+        // which the payoff stage carries into the sums (a NaN result, not a silently dropped path).
         bool have_np = false;
         float np = 0.0f;
         const uint32_t max_blocks = 64u * (uint32_t)L.N + 4096u;
+        const float inv_d = rcp_approx(pc.d);
         while (step < L.N) {
             if (blk > max_blocks) { V = __int_as_float(0x7fc00000); break; }
             const U4 w = next_block(blk++);
@@ -223,25 +260,25 @@ __device__ __forceinline__ void em_variance_path(const EmLaunch &L, const EmPoin
                     np = poisson_inversion(mu, u01_open(w.x));
                     have_np = true;
                 } else {
-                    have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), np);
+                    have_np = ptrs_trial(mu, u01_open(w.x), u01_open(w.y), lg2fact, np);
                 }
             }
-            if (have_np) {
-                const uint32_t a19 = ((w.x & 0x1ffu) << 10) | ((w.y & 0x1ffu) << 1) | ((w.z >> 8) & 1u);
-                const float rad = sqrt_approx(-1.38629436f * lg2_approx(u01_open(w.z)));      // sqrt(-2 ln u)
-                const float x = rad * sin_approx(__uint_as_float((a19 << 4) | 0x3f800000u) * 6.2831855f);
-                float shape = pc.d + np, boost = 1.0f;
-                if (shape < 1.0f) {
-                    const uint32_t b17 = ((w.z & 0xffu) << 9) | (w.w & 0x1ffu);
-                    const float ub = __uint_as_float((b17 << 6) | 0x3f800020u) - 1.0f;         // (k + 0.5) 2^-17
-                    boost = ex2_approx(lg2_approx(ub) / shape);
-                    shape += 1.0f;
-                }
-                const float md = shape - (1.0f / 3.0f);
-                const float mc = rsqrt_approx(9.0f * md);
-                float gam;
-                if (mt_trial(x, u01_open(w.w), md, mc, gam)) {
-                    const float Vn = __fmul_rn(pc.f_scale, 2.0f * gam * boost);   // f_scale = c / 2
+            {
+                const float shape0 = pc.d + np;
+                const bool small = shape0 < 1.0f;                      // only for N = 0: Gamma(d) = Gamma(d + 1) U^(1/d)
+                const float md = (small ? shape0 + 1.0f : shape0) - (1.0f / 3.0f);
+                const float rad = sqrt_approx(-lg2_approx(u01_open(w.z)));
+                const float ang = __uint_as_float(and_or(__funnelshift_r(w.w, w.z, 18), 0x7fffe0u, 0x3f800000u)) * 6.2831855f;
+                const float xs = (rad * (1.1774100f * rsqrt_approx(9.0f * md))) * cos_approx(ang);   // c0 rad cos / sqrt(9 md)
+                const float v1 = xs + 1.0f;
+                const float v = v1 * v1 * v1;
+                const float lv = lg2_approx(v);                        // v1 <= 0: NaN or -inf, the test below fails
+                const float rhs = md * fmaf(fmaf(4.5f * xs, xs, 1.0f - v), 1.44269504f, lv);
+                const float lu = lg2_approx(__uint_as_float(and_or(w.w, 0x7fffffu, 0x3f800000u)) - 0.99999994f);
+                const float boost = ex2_approx((lu - rhs) * inv_d);
+                const float gam = md * v * (small ? boost : 1.0f);
+                if (have_np && lu < rhs) {
+                    const float Vn = __fmul_rn(pc.scale, gam);
                     acc = __fadd_rn(acc, Vn);
                     V = Vn;
                     ++step;
@@ -270,6 +307,11 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
     asm volatile("" : "+r"(path_hi));                       // computed once, not re-derived from blockIdx in the loop
     const uint32_t stream = L.call0 + (uint32_t)point;      // ctr.y: one stream per compute() call / point
 
+    __shared__ float s_lg2fact[10];                        // log2(k!) for the Poisson sampler's small counts
+    if constexpr (KIND == kEmMixture || KIND == kEmAny) {
+        if (threadIdx.x < 10) s_lg2fact[threadIdx.x] = kLg2Factorial[threadIdx.x];
+        __syncthreads();
+    }
     float V = L.v0, acc = 0.0f, S = 0.0f;                  // acc = V_1 + ... + V_n so far
     {
         // counter = (trial block, stream, path_lo, path_hi): everything but the first word is fixed for this path
@@ -280,11 +322,11 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         };
         uint32_t blk = 0;
         if constexpr (KIND == kEmAny) {
-            if (pc.kind == kEmSplitPacked) em_variance_path<kEmSplitPacked>(L, pc, valid, next_block, V, acc, blk);
-            else if (pc.kind == kEmSplit) em_variance_path<kEmSplit>(L, pc, valid, next_block, V, acc, blk);
-            else em_variance_path<kEmMixture>(L, pc, valid, next_block, V, acc, blk);
+            if (pc.kind == kEmSplitPacked) em_variance_path<kEmSplitPacked>(L, pc, valid, next_block, s_lg2fact, V, acc, blk);
+            else if (pc.kind == kEmSplit) em_variance_path<kEmSplit>(L, pc, valid, next_block, s_lg2fact, V, acc, blk);
+            else em_variance_path<kEmMixture>(L, pc, valid, next_block, s_lg2fact, V, acc, blk);
         } else {
-            em_variance_path<KIND>(L, pc, valid, next_block, V, acc, blk);
+            em_variance_path<KIND>(L, pc, valid, next_block, s_lg2fact, V, acc, blk);
         }
         // terminal draw (NMCH_EM.cu:247-260, generalised to S_0, r, T)
         const U4 w = next_block(blk);
@@ -526,6 +568,8 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
     pt.f_t1 = (float)(c0 * std::sqrt(0.5 * cc));
     pt.f_ev = (float)e;
     pt.f_scale = 0.5f * pt.scale;
+    pt.f_hs = (pt.mt_c > 0.0f) ? (float)(0.5 * log2e / ((double)pt.mt_c * (double)pt.mt_c)) : 0.0f;   // (c0^2/2) log2 e / (mt_c c0)^2
+    pt.f_lg2s = (pt.mt_d > 0.0f) ? (float)std::log2((double)pt.mt_d * cc) : 0.0f;
     pt.k = kf;
     pt.ktheta_T = (float)(k * theta * (double)p.T);
     pt.inv_sigma = (float)(1.0 / sigma);
@@ -537,7 +581,7 @@ static EmPoint fold_em_point(const nmch_params_t &p, float kf, float thetaf, flo
 static bool em_point_finite(const EmPoint &pt)
 {
     const float v[] = {pt.scale, pt.lc, pt.d, pt.a, pt.mt_d, pt.mt_c, pt.inv_a, pt.f_c, pt.f_h, pt.f_dl,
-                       pt.f_g2s, pt.f_t1, pt.f_ev, pt.f_scale, pt.k, pt.ktheta_T, pt.inv_sigma};
+                       pt.f_g2s, pt.f_t1, pt.f_ev, pt.f_scale, pt.f_hs, pt.f_lg2s, pt.k, pt.ktheta_T, pt.inv_sigma};
     for (float x : v)
         if (!std::isfinite(x)) return false;
     return pt.scale > 0.0f && pt.lc > 0.0f;

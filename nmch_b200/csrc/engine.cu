@@ -262,11 +262,24 @@ int plan_xorwow_chunks(nmch_engine *e, cudaStream_t stream, int n_points, FeLaun
     L.chunk_points = n_points;
     L.n_chunks = 1;
     *skip = nullptr;
-    const unsigned long long target = (unsigned long long)(e->sm_count > 0 ? e->sm_count : 148) * 1536ull;   // threads that fill the GPU
-    if (n_points < 2 || e->n_local >= target) return NMCH_OK;
-    unsigned long long want = (target + e->n_local - 1ull) / e->n_local;
-    if (want > (unsigned long long)n_points) want = (unsigned long long)n_points;
-    L.chunk_points = (int)(((unsigned long long)n_points + want - 1ull) / want);
+    const unsigned long long sms = (unsigned long long)(e->sm_count > 0 ? e->sm_count : 148);
+    if (n_points < 2 || e->n_local >= sms * 1536ull) return NMCH_OK;            // the paths alone fill the GPU
+    // Points per chunk: the makespan is (blocks on the busiest SM) x (points a block walks), plus one skip-ahead per
+    // chunk (about 4 % of a 1000-step point).  More, shorter chunks balance the SMs better; pick the minimum.
+    const unsigned long long bpp = (unsigned long long)L.blocks_per_point;
+    double best = 0.0;
+    int best_cp = n_points;
+    const int cp_max = n_points < 256 ? n_points : 256;
+    for (int cp = 1; cp <= cp_max; ++cp) {
+        const unsigned long long chunks = ((unsigned long long)n_points + cp - 1) / cp;
+        if (chunks > 65535ull) continue;                                       // grid.y
+        const unsigned long long per_sm = (bpp * chunks + sms - 1ull) / sms;
+        // one path per thread, no ILP: an SM needs about 48 warps (6 blocks of 256) in flight to run at full rate
+        const double fill = per_sm >= 6ull ? 1.0 : (double)per_sm / 6.0;
+        const double cost = (double)per_sm * ((double)cp + 0.05) / fill;
+        if (cp == 1 || cost < best) { best = cost; best_cp = cp; }
+    }
+    L.chunk_points = best_cp;
     L.n_chunks = (n_points + L.chunk_points - 1) / L.chunk_points;
     if (L.n_chunks < 2) return NMCH_OK;
     const unsigned long long draws = 2ull * (unsigned long long)e->p.N * (unsigned long long)L.chunk_points;
