@@ -840,6 +840,217 @@ void orc_qe_run(const orc_params_t *p, uint64_t seed, uint64_t first_path, uint6
 }
 
 /* ======================================================================== */
+/* native EM sampler of the product (no reference counterpart: its scheme, own draws) */
+/* ======================================================================== */
+/* Restates nmch_b200/csrc/em_kernels.cu (em_native_kernel) on the SAME Philox words with libm in place of the MUFU
+ * approximations, so the kernel's bit fields, trial order, boost recycling and commit logic can be checked path by
+ * path (a flipped accept/reject re-routes a path: the tests ask for the overwhelming majority, and for the aggregate).
+ * The SCHEME is the reference's (NMCH_EM.cu:226-260: exact CIR transition per step, trapezoid integral, one
+ * conditional log-normal draw); the SAMPLER is the product's: chi-square split for d > 1/2, Poisson mixture below.
+ * counter = (trial block, call, path_lo, path_hi), key = seed.  In the split samplers the block counter is shared by
+ * the 32 paths of an aligned group (the kernel's loop is warp-uniform), so the terminal draw of a path sits behind the
+ * SLOWEST path of its group: paths are processed in aligned groups of 32 here too. */
+typedef struct {
+    float scale, lc, d, mt_d, inv_a, f_c, f_dl, f_g2s, f_t1, f_ev, f_hs, f_lg2s, k, ktheta_T, inv_sigma;
+    int kind;                                    /* 0 split + boost, 1 mixture, 2 split without boost */
+} em_native_point_t;
+
+static em_native_point_t em_native_fold(const orc_params_t *p)
+{
+    const double k = p->k, theta = p->theta, sigma = p->sigma, dt = (double)p->T / p->N;
+    const double e = exp(-k * dt), om = -expm1(-k * dt);
+    const double c0 = 1.1774100225154747, log2e = 1.4426950408889634;
+    em_native_point_t pt;
+    memset(&pt, 0, sizeof pt);
+    const double cc = sigma * sigma * om / (2.0 * k);
+    pt.scale = (float)cc;
+    pt.lc = (float)(2.0 * k * e / (sigma * sigma * om));
+    pt.d = (float)(2.0 * k * theta / (sigma * sigma));
+    double a = 2.0 * k * theta / (sigma * sigma) - 0.5;
+    const float af = (float)a;
+    float mt_c = 0.0f;
+    if (a > 0.0) {
+        if (a < 1.0) { pt.inv_a = (float)(1.0 / a); a += 1.0; }
+        const double md = a - 1.0 / 3.0;
+        pt.mt_d = (float)md;
+        mt_c = (float)(1.0 / sqrt(9.0 * md));
+    }
+    pt.f_c = (float)(mt_c * c0);
+    pt.f_dl = (float)(pt.mt_d * log2e);
+    pt.f_g2s = (float)(pt.mt_d * cc);
+    pt.f_t1 = (float)(c0 * sqrt(0.5 * cc));
+    pt.f_ev = (float)e;
+    pt.f_hs = (mt_c > 0.0f) ? (float)(0.5 * log2e / ((double)mt_c * (double)mt_c)) : 0.0f;
+    pt.f_lg2s = (pt.mt_d > 0.0f) ? (float)log2((double)pt.mt_d * cc) : 0.0f;
+    pt.k = p->k;
+    pt.ktheta_T = (float)(k * theta * (double)p->T);
+    pt.inv_sigma = (float)(1.0 / sigma);
+    pt.kind = !(af > 1e-3f) ? 1 : (pt.inv_a != 0.0f ? 0 : 2);
+    return pt;
+}
+
+static inline float em_u01(uint32_t w) { return ((float)(w >> 9) + 0.5f) * 1.1920929e-07f; }
+static inline float em_bits(uint32_t m) { union { uint32_t u; float f; } x; x.u = m | 0x3f800000u; return x.f; }
+
+/* one 64-bit split trial (em_split_trial): returns accept */
+static int em_native_split_trial(uint32_t wa, uint32_t wc, const em_native_point_t *pc, int boost, float *zp, float *g2)
+{
+    const float rad = sqrtf(-log2f(em_u01(wa)));
+    const float ang = em_bits(((wa << 14) | (wc >> 18)) & 0x7fffe0u) * 6.2831855f;
+    *zp = rad * sinf(ang);
+    const float xs = (rad * pc->f_c) * cosf(ang);
+    const float v1 = xs + 1.0f, v = v1 * v1 * v1;
+    const float lv = log2f(v);                                   /* v <= 0: NaN or -inf, the test fails */
+    float rhs = (xs * xs) * pc->f_hs;
+    rhs = fmaf(1.0f - v, pc->f_dl, rhs);
+    rhs = fmaf(lv, pc->mt_d, rhs);
+    const float lu = log2f(em_bits(wc & 0x7fffffu) - 0.99999994f);
+    *g2 = boost ? exp2f(fmaf(lu - rhs, pc->inv_a, lv + pc->f_lg2s)) : pc->f_g2s * v;
+    return lu < rhs;
+}
+
+static const float em_lg2fact[10] = {0.0f, 0.0f, 1.0f, 2.5849625f, 4.5849625f, 6.9068906f, 9.4918531f, 12.2992080f,
+                                     15.2992080f, 18.4691330f};
+
+static int em_native_ptrs(float mu, float u_raw, float v, float *k_out)
+{
+    const float kLn2 = 0.69314718f, kLog2e = 1.44269504f;
+    const float smu = sqrtf(mu), b = fmaf(2.53f, smu, 0.931f), a = fmaf(0.02483f, b, -0.059f);
+    const float inv_alpha = fmaf(1.1328f, 1.0f / (b - 3.4f), 1.1239f);
+    const float u = u_raw - 0.5f, us = 0.5f - fabsf(u), inv_us = 1.0f / us;
+    const float k = floorf(fmaf(fmaf(2.0f * a, inv_us, b), u, mu + 0.43f));
+    *k_out = k;
+    const int big = k >= 10.0f;
+    const float t = v * inv_alpha * (1.0f / fmaf(a * inv_us, inv_us, b));
+    const float lhs = 0.5f * log2f(big ? (t * t) * (6.28318531f * k) : t * t);
+    const float ik = 1.0f / (big ? k : 1.0f);
+    const float delta = (k - mu) * ik, sv = delta * (1.0f / (2.0f - delta)), s2 = sv * sv;
+    float poly = fmaf(s2, 1.0f / 11.0f, 1.0f / 9.0f);
+    poly = fmaf(poly, s2, 1.0f / 7.0f);
+    poly = fmaf(poly, s2, 1.0f / 5.0f);
+    poly = fmaf(poly, s2, 1.0f / 3.0f);
+    const float f_series = -fmaf(2.0f * sv * s2, poly, delta * sv);
+    const float lgx = log2f(big ? mu * ik : mu);
+    const float f_log = fmaf(lgx, kLn2, delta);
+    const float stirling = ik * fmaf(ik * ik, 1.0f / 360.0f, -1.0f / 12.0f);
+    const float rhs_big = fmaf(k, (fabsf(sv) < 0.3f) ? f_series : f_log, stirling) * kLog2e;
+    int ki = big ? 0 : (int)k;
+    if (ki < 0) ki = 0;
+    const float rhs_small = fmaf(k, lgx, -fmaf(mu, kLog2e, em_lg2fact[ki]));
+    const float rhs = big ? rhs_big : rhs_small;
+    return (k >= 0.0f) && !(us < 0.013f && v > us) && (lhs <= rhs);
+}
+
+static float em_native_terminal(const orc_params_t *p, const em_native_point_t *pc, const uint32_t w[4], float V, float acc)
+{
+    const float half_dt = 0.5f * (p->T / (float)p->N), one_m_rho2 = 1.0f - p->rho * p->rho;
+    const float lnS0_rT = (float)(log((double)p->S_0) + (double)p->r * (double)p->T);
+    const float r = sqrtf(-1.38629436f * log2f(em_u01(w[0])));
+    const float z = r * sinf(em_bits(w[1] >> 9) * 6.2831855f);
+    const float vI = fmaf(2.0f, acc, p->v_0 - V) * half_dt;
+    float m = pc->inv_sigma * fmaf(pc->k, vI, V - p->v_0 - pc->ktheta_T);
+    m = fmaf(p->rho, m, fmaf(-0.5f, vI, lnS0_rT));
+    return expf(fmaf(sqrtf(one_m_rho2 * vI), z, m));
+}
+
+void orc_em_native_run(const orc_params_t *p, uint64_t seed, uint64_t first_path, uint64_t n_paths, uint32_t call,
+                       float *S_out, float *V_out, double *sum, double *sumsq, int threads)
+{
+    const em_native_point_t pc = em_native_fold(p);
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const float K = p->S_0;
+    const int N = p->N;
+    double acc_sum = 0.0, acc_sq = 0.0;
+    if (threads <= 0) threads = orc_max_threads();
+    const uint64_t g_begin = first_path, g_end = first_path + n_paths;
+    const int64_t grp0 = (int64_t)(g_begin / 32u), grp1 = (int64_t)((g_end + 31u) / 32u);
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc_sum, acc_sq) num_threads(threads) schedule(dynamic, 8)
+#endif
+    for (int64_t grp = grp0; grp < grp1; ++grp) {
+        float Vt[32], At[32];
+        uint32_t blk_end[32];
+        uint32_t blk_group = 0;
+        for (int lane = 0; lane < 32; ++lane) {
+            const uint64_t g = (uint64_t)grp * 32u + (uint64_t)lane;
+            blk_end[lane] = 0;
+            if (g < g_begin || g >= g_end) continue;
+            uint32_t ctr[4] = {0, call, (uint32_t)g, (uint32_t)(g >> 32)}, w[8];
+            float V = p->v_0, acc = 0.0f;
+            int step = 0;
+            uint32_t blk = 0;
+            if (pc.kind != 1) {
+                while (step < N) {                                /* two blocks = four trials per iteration */
+                    ctr[0] = blk; orc_philox4x32_10(ctr, key, w);
+                    ctr[0] = blk + 1u; orc_philox4x32_10(ctr, key, w + 4);
+                    blk += 2u;
+                    for (int j = 0; j < 4; ++j) {
+                        float zp, g2;
+                        const int ok = em_native_split_trial(w[2 * j], w[2 * j + 1], &pc, pc.kind == 0, &zp, &g2);
+                        const float t = fmaf(pc.f_t1, zp, sqrtf(pc.f_ev * V));
+                        const float Vn = fmaf(t, t, g2);
+                        if (ok && step < N) { acc += Vn; V = Vn; ++step; }
+                    }
+                }
+                if (blk > blk_group) blk_group = blk;             /* the group ends with its slowest path */
+            } else {
+                int have_np = 0;
+                float np = 0.0f;
+                const float inv_d = 1.0f / pc.d;
+                while (step < N) {
+                    ctr[0] = blk++; orc_philox4x32_10(ctr, key, w);
+                    if (!have_np) {
+                        const float mu = pc.lc * V;
+                        if (mu < 10.0f) {
+                            float pp = exp2f(-1.44269504f * mu), cdf = pp, kk = 0.0f;
+                            const float u = em_u01(w[0]);
+                            while (u > cdf && kk < 80.0f) { kk += 1.0f; pp *= mu * (1.0f / kk); cdf += pp; }
+                            np = kk;
+                            have_np = 1;
+                        } else {
+                            have_np = em_native_ptrs(mu, em_u01(w[0]), em_u01(w[1]), &np);
+                        }
+                    }
+                    const float shape0 = pc.d + np;
+                    const int small = shape0 < 1.0f;
+                    const float md = (small ? shape0 + 1.0f : shape0) - (1.0f / 3.0f);
+                    const float rad = sqrtf(-log2f(em_u01(w[2])));
+                    const float ang = em_bits(((w[2] << 14) | (w[3] >> 18)) & 0x7fffe0u) * 6.2831855f;
+                    const float xs = (rad * (1.1774100f * (1.0f / sqrtf(9.0f * md)))) * cosf(ang);
+                    const float v1 = xs + 1.0f, v = v1 * v1 * v1, lv = log2f(v);
+                    const float rhs = md * fmaf(fmaf(4.5f * xs, xs, 1.0f - v), 1.44269504f, lv);
+                    const float lu = log2f(em_bits(w[3] & 0x7fffffu) - 0.99999994f);
+                    const float boost = exp2f((lu - rhs) * inv_d);
+                    const float gam = md * v * (small ? boost : 1.0f);
+                    if (have_np && lu < rhs) {
+                        const float Vn = pc.scale * gam;
+                        acc += Vn; V = Vn; ++step; have_np = 0;
+                    }
+                }
+                blk_end[lane] = blk;                              /* per-lane counter in the mixture loop */
+            }
+            Vt[lane] = V;
+            At[lane] = acc;
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+            const uint64_t g = (uint64_t)grp * 32u + (uint64_t)lane;
+            if (g < g_begin || g >= g_end) continue;
+            const uint32_t ctr[4] = {pc.kind != 1 ? blk_group : blk_end[lane], call, (uint32_t)g, (uint32_t)(g >> 32)};
+            uint32_t w[4];
+            orc_philox4x32_10(ctr, key, w);
+            const float S = em_native_terminal(p, &pc, w, Vt[lane], At[lane]);
+            const float pay = fmaxf(0.0f, S - K);
+            acc_sum += (double)pay;
+            acc_sq += (double)pay * (double)pay;
+            if (S_out) S_out[g - g_begin] = S;
+            if (V_out) V_out[g - g_begin] = Vt[lane];
+        }
+    }
+    if (sum) *sum = acc_sum;
+    if (sumsq) *sumsq = acc_sq;
+}
+
+/* ======================================================================== */
 /* host statistics                                                           */
 /* ======================================================================== */
 float orc_get_err(int state_numbers, float strike_price, float price_squared)

@@ -124,6 +124,8 @@ double orc_heston_call(double S0, double K, double v0, double r, double kappa,
  * Returns the number of points written (<= cap). */
 int orc_exploration_grid(int steps, int apply_filter, float *k, float *theta, float *sigma, int cap);
 
+void orc_em_native_run(const orc_params_t *p, uint64_t seed, uint64_t first_path, uint64_t n_paths, uint32_t call,
+                       float *S_out, float *V_out, double *sum, double *sumsq, int threads);
 uint64_t orc_rng_init_only(int rng_kind, uint64_t seed, uint64_t first_path, uint64_t n_paths, int threads);
 int orc_max_threads(void);
 

@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
                                  C.c_int, f32p, f32p, f64p, f64p, C.c_int]
         L.orc_qe_run.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, f32p, f32p, f64p,
                                  f64p, C.c_int]
+        L.orc_em_native_run.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, f32p, f32p, f64p,
+                                        f64p, C.c_int]
         L.orc_em_exact_run.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint64, f64p, f64p, f64p, C.c_int]
         L.orc_get_err.argtypes = [C.c_int, C.c_float, C.c_float]
         L.orc_get_err.restype = C.c_float
@@ -213,6 +215,18 @@ def qe_run(p: Params, seed=1234, first_path=0, n_paths=1024, call=0, want_paths=
     cp = p.c()
     lib().orc_qe_run(C.byref(cp), seed, first_path, n_paths, call, _fp(S, C.c_float), _fp(V, C.c_float), C.byref(s),
                      C.byref(s2), threads)
+    return {"sum": s.value, "sumsq": s2.value, "n": n_paths, "mean": s.value / n_paths, "mean_sq": s2.value / n_paths,
+            "S": S, "V": V}
+
+
+def em_native_run(p: Params, seed=1234, first_path=0, n_paths=1024, call=0, want_paths=False, threads=0):
+    """The product's native EM sampler restated on the kernel's own Philox words (checker for em_native_kernel)."""
+    S = np.empty(n_paths, np.float32) if want_paths else None
+    V = np.empty(n_paths, np.float32) if want_paths else None
+    s, s2 = C.c_double(), C.c_double()
+    cp = p.c()
+    lib().orc_em_native_run(C.byref(cp), seed, first_path, n_paths, call, _fp(S, C.c_float), _fp(V, C.c_float), C.byref(s),
+                            C.byref(s2), threads)
     return {"sum": s.value, "sumsq": s2.value, "n": n_paths, "mean": s.value / n_paths, "mean_sq": s2.value / n_paths,
             "S": S, "V": V}
 

@@ -36,6 +36,10 @@ def em_engine(n, N=1000, rng=0, **kw):
     return E.Engine(NTPB=ntpb, NB=n // ntpb, N=N, method=E.METHOD_EM, rng=rng, **kw)
 
 
+def em_engine_n(n, N, **kw):
+    return E.Engine(NTPB=1, NB=1, N=N, method=E.METHOD_EM, n_paths=n, **kw)
+
+
 def _ref_cuda(**flags):
     exe = o.REF_HARNESS_PATH
     if not os.path.exists(exe):
@@ -110,6 +114,37 @@ def test_native_matches_analytic_and_martingale():
     ref = o.em_exact_run(o.Params(), seed=3, n_paths=1 << 16)
     se = np.hypot(m.std_error, o.std_error(ref["mean"], ref["mean_sq"], 1 << 16))
     assert abs(m.mean - ref["mean"]) < 3 * se
+
+
+@pytest.mark.parametrize("k,theta,sigma", [
+    (0.5, 0.1, 0.3),             # split, boost recycled from the accept test (the README point)
+    (0.5, 0.1, 0.42),            # split, boosted gamma of shape 0.067
+    (2.08, 0.108, 0.28),         # split without boost
+    (2.08, 0.108, 1.0),          # Poisson mixture: PTRS + inversion + per-lane gamma shape
+    (0.1, 0.5, 1.0),             # Poisson mixture, d = 0.1
+])
+def test_native_tracks_the_oracle_restatement_per_path(k, theta, sigma):
+    """The native sampler against the oracle's restatement of ITS mapping (same Philox words, bit fields, trial order,
+    recycled boost, commit logic, block counter shared by aligned groups of 32 paths; libm instead of MUFU).  A flipped
+    accept/reject re-routes a path, so: the overwhelming majority of paths to 2e-3, the aggregate to a fraction of an SE.
+    Two consecutive calls (two streams), a ragged path count, and a shard that starts at path 4096."""
+    n, N = 4096 + 37, 60
+    p = o.Params(N=N, k=k, theta=theta, sigma=sigma)
+    with em_engine_n(n, N, k=k, theta=theta, sigma=sigma) as e:
+        e.init(4321)
+        for call in range(2):
+            S, V, m = e.compute_paths()
+            ref = o.em_native_run(p, seed=4321, n_paths=n, call=call, want_paths=True)
+            close = np.isclose(S, ref["S"], rtol=2e-3, atol=2e-4) & np.isclose(V, ref["V"], rtol=2e-3, atol=1e-5)
+            assert close.mean() > 0.98, (call, close.mean())
+            se = o.std_error(ref["mean"], ref["mean_sq"], n)
+            assert abs(m.mean - ref["mean"]) < 0.5 * se, (call, m.mean, ref["mean"], se)
+    with E.Engine(NTPB=1, NB=1, N=N, method=E.METHOD_EM, n_paths=3 * 4096, first_path=4096, n_local=1000, k=k, theta=theta,
+                  sigma=sigma) as e:
+        e.init(4321)
+        S, V, m = e.compute_paths()
+    ref = o.em_native_run(p, seed=4321, first_path=4096, n_paths=1000, want_paths=True)
+    assert np.isclose(S, ref["S"], rtol=2e-3, atol=2e-4).mean() > 0.98
 
 
 @pytest.mark.parametrize("k,theta,sigma,v0", [

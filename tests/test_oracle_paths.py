@@ -134,3 +134,23 @@ def test_qe_restatement_matches_semi_analytic_at_large_steps():
         se = o.std_error(r["mean"], r["mean_sq"], n)
         assert abs(r["mean"] - want) < 3.5 * se + 3e-4
         assert abs(r["S"].astype(np.float64).mean() - 1.0) < 4 * r["S"].std() / np.sqrt(n)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(k=2.08, theta=0.108, sigma=0.28), dict(k=2.08, theta=0.108, sigma=1.0),
+                                dict(k=0.5, theta=0.1, sigma=0.42)])
+def test_native_em_restatement_is_statistically_exact(kw):
+    """oracle.em_native_run restates the product's native EM sampler (the GPU test checks the kernel against it path by
+    path); on its own it must price the option and keep the martingale and E[V_T] -- for all three samplers."""
+    n = 1 << 16
+    p = o.Params(N=100, **kw)
+    r = o.em_native_run(p, seed=99, n_paths=n, want_paths=True)
+    want = o.heston_call(kappa=p.k, theta=p.theta, sigma=p.sigma)
+    se = o.std_error(r["mean"], r["mean_sq"], n)
+    assert abs(r["mean"] - want) < 3.5 * se + 1e-4, (r["mean"], want, se)
+    S = r["S"].astype(np.float64)
+    V = r["V"].astype(np.float64)
+    assert abs(S.mean() - 1.0) < 4 * S.std() / np.sqrt(n) + 1e-4
+    assert abs(V.mean() - (p.theta + (0.1 - p.theta) * np.exp(-p.k))) < 4 * V.std() / np.sqrt(n) + 1e-5
+    # a second call is a different stream
+    r2 = o.em_native_run(p, seed=99, n_paths=1024, call=1, want_paths=True)
+    assert not np.array_equal(r2["S"], r["S"][:1024])
