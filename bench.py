@@ -218,6 +218,10 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3, with_o
             from nmch_b200 import engine as E
             # same seed, same calls through OUR draw-compatible stream mode: identical draws, our timing
             same_seed(E.RNG_XORWOW_COMPAT if rng == "xorwow" else E.RNG_PHILOX_COMPAT, "ours_same_draws")
+            if rng == "philox" and method == "fe":
+                # the DEFAULT fast mode consumes the same Philox words and forms the same uniforms as the reference's
+                # Philox instantiation: its own same-seed difference, at its own speed
+                same_seed(E.RNG_PHILOX, "ours_native_same_words")
             if rng == "xorwow" and method == "fe":
                 # the same integer draws through the native fast-math step (opt-in NMCH_RNG_XORWOW_FAST)
                 same_seed(E.RNG_XORWOW_FAST, "ours_same_stream_fast")
@@ -238,7 +242,8 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3, with_o
         out["what"] += ("; ours_same_draws = this engine in the draw-compatible VALIDATION mode for that tag, same seed and "
                         "calls (a checker, not a performance mode: it runs the reference's IEEE transforms); "
                         "ours_same_stream_fast = the same XORWOW integer draws through the native fast-math step "
-                        "(NMCH_RNG_XORWOW_FAST); max_rel_diff_* against run 1 of the reference and against the mean "
+                        "(NMCH_RNG_XORWOW_FAST); ours_native_same_words (Philox tag) = the DEFAULT native mode, which "
+                        "consumes the same Philox words and uniforms with fast transforms; max_rel_diff_* against run 1 of the reference and against the mean "
                         "of its runs, to be read against own_spread")
     return out
 

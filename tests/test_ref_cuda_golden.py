@@ -79,6 +79,26 @@ def test_engine_compat_reproduces_reference_cuda(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["flags"]["method"] == "fe" and c["flags"]["rng"] == "philox"],
+                         ids=lambda c: "{method}-{rng}-{NTPB}x{NB}-N{N}".format(**c["flags"]))
+def test_engine_NATIVE_mode_reproduces_reference_cuda_philox(case):
+    """The default fast mode (NMCH_RNG_PHILOX: MUFU transforms, folded step) against the reference's CUDA build of its
+    Philox instantiation (the reference CLI's default, nmch.cu:119,130) on the same seed and consecutive calls.  Round 2
+    feeds cuRAND's own uniforms into the fast transforms, so the north star's 1e-5 tolerance of the draw-COMPATIBLE
+    mode holds for the fast mode too -- at 2.9x the reference's speed."""
+    from nmch_b200 import engine as E
+    f = case["flags"]
+    kw = {k: f[k] for k in PKEYS if k in f}
+    with E.Engine(NTPB=f["NTPB"], NB=f["NB"], N=f["N"], rng=E.RNG_PHILOX, **kw) as e:
+        e.init(1234)
+        for want in case["calls"]:
+            m = e.compute()
+            var_ref = want["E2"] - want["E"] ** 2
+            assert _rel(m.mean, want["E"]) < 1e-5 + 4 * want["E_spread"] / want["E"], (m.mean, want)
+            assert _rel(m.variance, var_ref) < 1e-5 + 4 * want["E2_spread"] / var_ref, (m.variance, var_ref)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("sw", GOLD["sweeps"], ids=lambda s: s["flags"]["method"])
 def test_engine_compat_sweep_reproduces_reference_cuda(sw):
     from nmch_b200 import engine as E
