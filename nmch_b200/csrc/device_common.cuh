@@ -89,30 +89,63 @@ __device__ __forceinline__ PhiloxPathInv philox_path_invariants(uint32_t block_h
     return v;
 }
 
+// The part of a block that depends on neither the path's low word nor the thread: from s = M0 * block_lo and the
+// (block-uniform) high path word.  Everything here is the same for every thread of the block, so it belongs on the
+// uniform datapath; it is grouped so that each per-path LOP3 of rounds 2-3 sees ONE uniform operand (two uniform
+// operands of one LOP3 would force ptxas to keep the whole chain, multiplies included, in vector registers).
+struct PhiloxBlockUniform {
+    uint32_t c0u;        // hi(M1 * c2') ^ k0[1]      with c2' = hi(s) ^ path_hi ^ k1[0]   -> c0 entering round 2 is c0u ^ inv.lo1
+    uint32_t c1u;        // lo(M1 * c2') ^ k0[2]      c1 entering round 2, with round 3's key already folded in
+    uint32_t c2u;        // lo(s) ^ k1[1]             c2 entering round 2 is inv.q_hi ^ c2u
+};
+
+__device__ __forceinline__ PhiloxBlockUniform philox_block_uniform(uint32_t block_lo, uint32_t path_hi, const PhiloxKeys &K)
+{
+    const unsigned long long s = (unsigned long long)kPhiloxM0 * block_lo;
+    const uint32_t c2_r1 = (uint32_t)(s >> 32) ^ path_hi ^ K.k1[0];
+    const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2_r1;
+    return PhiloxBlockUniform{(uint32_t)(p1 >> 32) ^ K.k0[1], (uint32_t)p1 ^ K.k0[2], (uint32_t)s ^ K.k1[1]};
+}
+
+__device__ __forceinline__ U4 philox4x32_10_hoisted(const PhiloxBlockUniform &bu, const PhiloxPathInv &inv, const PhiloxKeys &K)
+{
+    // state entering round 2 (index 1): (c0, c1, c2, c3) = (hi1^lo1'^k0[1], lo(p1), q_hi^lo(s)^k1[1], q_lo)
+    uint32_t c0 = bu.c0u ^ inv.lo1;
+    uint32_t c2 = inv.q_hi ^ bu.c2u;
+    uint32_t c3 = inv.q_lo;
+    // round 3 (index 2), with c1 ^ k0[2] pre-folded into the uniform word
+    {
+        const unsigned long long a = (unsigned long long)kPhiloxM0 * c0;
+        const unsigned long long b = (unsigned long long)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(b >> 32) ^ bu.c1u;
+        const uint32_t n2 = (uint32_t)(a >> 32) ^ c3 ^ K.k1[2];
+        c3 = (uint32_t)a;
+        c0 = n0;
+        c2 = n2;
+        uint32_t c1 = (uint32_t)b;
+#pragma unroll
+        for (int r = 3; r < 10; ++r) {
+            const unsigned long long a2 = (unsigned long long)kPhiloxM0 * c0;
+            const unsigned long long b2 = (unsigned long long)kPhiloxM1 * c2;
+            const uint32_t m0 = (uint32_t)(b2 >> 32) ^ c1 ^ K.k0[r];
+            const uint32_t m2 = (uint32_t)(a2 >> 32) ^ c3 ^ K.k1[r];
+            c1 = (uint32_t)b2;
+            c3 = (uint32_t)a2;
+            c0 = m0;
+            c2 = m2;
+        }
+        return U4{c0, c1, c2, c3};
+    }
+}
+
 // s_hi:s_lo = M0 * block_lo (computed once per thread and iteration), path_hi as in the counter.
 __device__ __forceinline__ U4 philox4x32_10_hoisted(uint32_t s_hi, uint32_t s_lo, uint32_t path_hi,
                                                     const PhiloxPathInv &inv, const PhiloxKeys &K)
 {
-    // state after round 1: (c0, c1, c2, c3) = (hi1^c1^k0[0], lo1, hi0^c3^k1[0], lo0)
-    //   -> round 2 needs M0*c0 (= inv.q) and M1*c2 with c2 = s_hi ^ path_hi ^ k1[0] (shared by the thread's paths)
     const uint32_t c2_r1 = s_hi ^ path_hi ^ K.k1[0];
     const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2_r1;
-    uint32_t c0 = (uint32_t)(p1 >> 32) ^ inv.lo1 ^ K.k0[1];
-    uint32_t c1 = (uint32_t)p1;
-    uint32_t c2 = inv.q_hi ^ s_lo ^ K.k1[1];
-    uint32_t c3 = inv.q_lo;
-#pragma unroll
-    for (int r = 2; r < 10; ++r) {
-        const unsigned long long a = (unsigned long long)kPhiloxM0 * c0;
-        const unsigned long long b = (unsigned long long)kPhiloxM1 * c2;
-        const uint32_t n0 = (uint32_t)(b >> 32) ^ c1 ^ K.k0[r];
-        const uint32_t n2 = (uint32_t)(a >> 32) ^ c3 ^ K.k1[r];
-        c1 = (uint32_t)b;
-        c3 = (uint32_t)a;
-        c0 = n0;
-        c2 = n2;
-    }
-    return U4{c0, c1, c2, c3};
+    const PhiloxBlockUniform bu{(uint32_t)(p1 >> 32) ^ K.k0[1], (uint32_t)p1 ^ K.k0[2], s_lo ^ K.k1[1]};
+    return philox4x32_10_hoisted(bu, inv, K);
 }
 
 // ---------------------------------------------------------------------------------------

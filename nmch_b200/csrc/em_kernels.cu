@@ -317,8 +317,7 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
         // counter = (trial block, stream, path_lo, path_hi): everything but the first word is fixed for this path
         const PhiloxPathInv inv = philox_path_invariants(stream, path_lo, L.keys);
         auto next_block = [&](uint32_t b) {
-            const unsigned long long s = (unsigned long long)kPhiloxM0 * b;
-            return philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv, L.keys);
+            return philox4x32_10_hoisted(philox_block_uniform(b, path_hi, L.keys), inv, L.keys);
         };
         uint32_t blk = 0;
         if constexpr (KIND == kEmAny) {

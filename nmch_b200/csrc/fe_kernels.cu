@@ -110,7 +110,8 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
         const unsigned long long local0 = tile * TILE;
         if (local0 >= L.n_local) break;
         const unsigned long long g0 = L.first_path + local0;     // multiple of TILE: no carry below
-        const uint32_t path_hi = (uint32_t)(g0 >> 32);
+        uint32_t path_hi = (uint32_t)(g0 >> 32);
+        asm volatile("" : "+r"(path_hi));                         // one register, not re-derived from the tile index in the loop
         const uint32_t path_lo0 = (uint32_t)g0 + threadIdx.x;
         NMCHB_ASSERT(((g0 + (unsigned long long)(TILE - 1)) >> 32) == (g0 >> 32));   // the tile's paths share path_hi
 
@@ -122,15 +123,16 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
         }
         unsigned long long blk = w0 >> 2;
         int n = L.N;
-        if (half_start && n > 0) {                                // resume in the middle of a block
+        const bool resume = half_start && n > 0;                  // resume in the middle of a block
+        if (resume) {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * THREADS, path_hi, L.keys);
                 fe_step_any<FLOOR, EXACT>(S[j], V[j], w.z, w.w, L, pc);
             }
-            ++blk;
-            --n;
         }
+        blk += resume ? 1ull : 0ull;                              // launch-uniform counters stay outside the branch
+        n -= resume ? 1 : 0;
         // Full blocks, two steps each.  The loop is split where the low counter word would wrap so that the
         // high word is loop-invariant: Philox round 1 and the per-path multiply of round 2 then depend only on
         // (path, high word) and are hoisted; the multiplies on the low word are shared by the thread's P paths.
@@ -145,10 +147,10 @@ fe_philox_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__
             for (int j = 0; j < P; ++j) inv[j] = philox_path_invariants(blk_hi, path_lo0 + j * THREADS, L.keys);
 #pragma unroll 1
             for (int it = 0; it < chunk; ++it) {
-                const unsigned long long s = (unsigned long long)kPhiloxM0 * (blk_lo + (uint32_t)it);   // uniform datapath
+                const PhiloxBlockUniform bu = philox_block_uniform(blk_lo + (uint32_t)it, path_hi, L.keys);   // uniform datapath
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
-                    const U4 w = philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv[j], L.keys);
+                    const U4 w = philox4x32_10_hoisted(bu, inv[j], L.keys);
                     fe_step_any<FLOOR, EXACT>(S[j], V[j], w.x, w.y, L, pc);
                     fe_step_any<FLOOR, EXACT>(S[j], V[j], w.z, w.w, L, pc);
                 }
@@ -296,10 +298,10 @@ fe_dense_kernel(const __grid_constant__ FeLaunch L, const FePoint *__restrict__ 
             for (int j = 0; j < P; ++j) inv[j] = philox_path_invariants(blk_hi, path_lo0 + j * THREADS, L.keys);
 #pragma unroll 1
             for (int it = 0; it < chunk; ++it) {
-                const unsigned long long s = (unsigned long long)kPhiloxM0 * (blk_lo + (uint32_t)it);
+                const PhiloxBlockUniform bu = philox_block_uniform(blk_lo + (uint32_t)it, path_hi, L.keys);
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
-                    const U4 w = philox4x32_10_hoisted((uint32_t)(s >> 32), (uint32_t)s, path_hi, inv[j], L.keys);
+                    const U4 w = philox4x32_10_hoisted(bu, inv[j], L.keys);
                     fe_step_dense<FLOOR>(S[j], V[j], w, 0, L, pc);
                     fe_step_dense<FLOOR>(S[j], V[j], w, 1, L, pc);
                     fe_step_dense<FLOOR>(S[j], V[j], w, 2, L, pc);
