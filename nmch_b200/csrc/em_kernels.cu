@@ -296,12 +296,18 @@ em_native_kernel(const __grid_constant__ EmLaunch L, const EmPoint *__restrict__
 {
     const EmPoint pc = (pts != nullptr) ? pts[blockIdx.y] : L.pt0;
     const int point = pc.index;
-    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // Paths of this block.  Written with the literal block size for the boosted split sampler and with blockDim.x for
+    // the others: with the literal, ptxas keeps the two path-independent Philox multiplies of every block on the uniform
+    // datapath (32 instead of 34 vector IMAD.WIDE per four trials) at the price of a few register moves -- measured on one
+    // box (scripts/r02_em_ab.py): boosted 9.86 -> 9.74 ms, but unboosted 8.97 -> 9.10 and mixture 36.6 -> 37.6, so each
+    // instantiation takes the form that is faster for it.
+    const unsigned long long block0 = (KIND == kEmSplit) ? (unsigned long long)blockIdx.x * kEmThreads
+                                                         : (unsigned long long)blockIdx.x * blockDim.x;
+    const unsigned long long idx = block0 + threadIdx.x;
     const bool valid = idx < L.n_local;
-    NMCHB_ASSERT(point >= 0 && point < L.n_points);
-    // first_path is a multiple of 4096 (checked at create): the high counter word is the same for the whole
-    // block, so the multiplies of a Philox block that do not depend on the path stay on the uniform datapath
-    const unsigned long long g0 = L.first_path + (unsigned long long)blockIdx.x * blockDim.x;
+    NMCHB_ASSERT(point >= 0 && point < L.n_points && blockDim.x == kEmThreads);
+    // first_path is a multiple of 4096 (checked at create): the high counter word is the same for the whole block
+    const unsigned long long g0 = L.first_path + block0;
     const uint32_t path_lo = (uint32_t)g0 + threadIdx.x;
     uint32_t path_hi = (uint32_t)(g0 >> 32);
     asm volatile("" : "+r"(path_hi));                       // computed once, not re-derived from blockIdx in the loop
