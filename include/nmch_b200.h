@@ -67,7 +67,7 @@ typedef struct {
     unsigned long long first_path;  /* shard: this engine simulates paths [first_path, first_path+n_local) */
     unsigned long long n_local;     /* auto(0) = n_paths - first_path */
     int   paths_per_thread;         /* auto(0): picked from n_local; 1, 2, 4 or 8 */
-    int   block_threads;            /* auto(0) = 128; 128 or 256 */
+    int   block_threads;            /* auto(0) = 256; 128 or 256 */
 } nmch_params_t;
 
 /* Replaces the two managed floats `sum[2]` (NMCH_FE.cu:376, 544-545) with raw FP64 sums:

@@ -510,7 +510,7 @@ static int engine_init_impl(nmch_engine_t *e, unsigned long long seed)
     e->seed = seed;
     e->draw_offset = 0;
     e->em_calls = 0;
-    e->threads = e->p.block_threads ? e->p.block_threads : 128;
+    e->threads = e->p.block_threads ? e->p.block_threads : 256;     // 256: 24.61 vs 24.69 ms at configs[1] (profiles/r02_fe_ab.txt)
     if (e->p.rng == NMCH_RNG_XORWOW_COMPAT || e->p.rng == NMCH_RNG_XORWOW_FAST) {
         const size_t n = (size_t)e->n_local;
         CU_TRY(xorwow_tables_create(&e->xtab));

@@ -65,7 +65,7 @@ CASES = textwrap.dedent(r"""
 
     # sweeps: several tiles per block (tiles > 256 with more than one point), ragged, many points
     def sweep_tiles():
-        with E.Engine(NTPB=1, NB=1, N=3, n_paths=300 * 512 + 77) as e:      # 301 tiles of 512 paths at P = 4
+        with E.Engine(NTPB=1, NB=1, N=3, n_paths=300 * 1024 + 77) as e:     # 301 tiles of 1024 paths at P = 4
             e.init(7)
             out = e.explore(grid_k[:3], grid_t[:3], grid_s[:3])
             assert len(out) == 3 and all(np.isfinite(m.sum_payoff) for m in out)

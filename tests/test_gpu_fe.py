@@ -384,11 +384,11 @@ def test_explore_with_several_tiles_per_block_matches_sequential():
     # many points x many path tiles: blocks walk several tiles each (a different reduction tree than a single compute)
     k, th, sg = o.exploration_grid(5, apply_filter=True)
     k, th, sg = k[:3], th[:3], sg[:3]
-    n, N = 1 << 18, 40
+    n, N = 1 << 19, 40                                            # 512 tiles of 4 x 256 paths: two tiles per block
     with E.Engine(NTPB=512, NB=n // 512, N=N, rng=0) as e:
         e.init(1234)
         batched = e.explore(k, th, sg)
-        assert e.launch_info()["grid_x"] <= 256 and e.launch_info()["grid_y"] == 3
+        assert e.launch_info()["grid_x"] == 256 and e.launch_info()["grid_y"] == 3
     with E.Engine(NTPB=512, NB=n // 512, N=N, rng=0) as e:
         e.init(1234)
         for i in range(3):
