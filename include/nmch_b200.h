@@ -48,7 +48,7 @@ typedef enum { NMCH_FLOOR_ABS = 0, NMCH_FLOOR_PLUS = 1 } nmch_floor;
  *                  own mapping and against the semi-analytic price)
  *   XORWOW_FAST    opt-in FE mode on the reference's default stream: the SAME cuRAND-XORWOW integer draws per path
  *                  as XORWOW_COMPAT (same seed scramble, subsequence skip-ahead and continuation across compute()
- *                  calls), pushed through the native fast-math step (23-bit uniforms, MUFU transforms) instead of
+ *                  calls), pushed through the native fast-math step (cuRAND's uniforms, MUFU transforms) instead of
  *                  cuRAND's IEEE transforms.  Prices agree with the reference's CUDA build on identical seeds to
  *                  ~1e-6 relative (the 1e-5 tolerance of the XORWOW-compatible mode) at 2.5x its speed; per-path
  *                  values agree to ~1e-4, not to the last bits -- use XORWOW_COMPAT for draw-for-draw validation */

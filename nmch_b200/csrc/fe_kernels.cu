@@ -504,8 +504,8 @@ fe_compat_kernel(const __grid_constant__ FeLaunch L, const RawPoint *__restrict_
 
 // ------------------------------------------------------------------------------------------
 // XORWOW stream + native step (opt-in mode NMCH_RNG_XORWOW_FAST): the reference's default generator, and therefore
-// the same integer draws per path as its CUDA build on the same seed, but the native arithmetic -- bit-spliced
-// 23-bit uniforms, MUFU Box-Muller sharing its square root with the SDE, folded constants.  XORWOW needs no
+// the same integer draws per path as its CUDA build on the same seed, but the native arithmetic -- cuRAND's uniforms
+// by I2FP + FFMA, MUFU Box-Muller sharing its square root with the SDE, folded constants.  XORWOW needs no
 // multiplies (8 ALU-pipe operations per draw), so the FMA pipe that binds the Philox kernels is left to the 11 FP32
 // operations of the step: 37.8 cycles per warp-step.  One path per thread (six state words in registers), the step
 // loop unrolled by five so that the rotation of the five xorshift words costs no moves; the points of a sweep are
