@@ -18,6 +18,7 @@ allreduce of the two FP64 moments per step when N>1.
 BASELINE.json's metric has a second half and a second workload, carried as sub-records of the same line at every N:
   em         configs[2]: EM exact scheme, N=1000, 2^22 paths per GPU (weak): paths/s, ms_per_step, roofline, e2e
   c5_strong  configs[4]: FE and EM at 2^30 GLOBAL paths sharded over the N ranks (strong scaling), 3 steps each
+  other_floor (N=1)  configs[1] names both variance floors: the (.)+ floor on the headline workload
   group_check (N>1)  the single-process group front end (nmch_group_*: ncclCommInitAll, what the C++ classes and
              `--gpus` use) over the same N devices, run by rank 0 after the timed regions: its sums against the
              torch.distributed path's and its time per step
@@ -535,6 +536,20 @@ def main():
         if world == 1 and args.method == "fe" and args.rng == "philox" and not args.no_sub_records:
             peak = line["roofline"]["peak"]
             units_per_gpu_step = n_per_gpu * N
+            try:                                  # configs[1] names both floors: the other one, same workload
+                other = E.FLOOR_PLUS if args.floor == "abs" else E.FLOOR_ABS
+                with E.Engine(NTPB=512, NB=n_per_gpu // 512, N=N, rng=E.RNG_PHILOX, device=local_rank, floor=other, **README) as fe2:
+                    fe2.init(1234)
+                    fe2.compute()
+                    runs = [fe2.compute() for _ in range(3)]
+                fms = min(r_.exec_ms for r_ in runs)
+                line["other_floor"] = {"floor": "plus" if args.floor == "abs" else "abs", "value": units_per_gpu_step / (fms * 1e-3),
+                                       "unit": unit, "ms_per_step": fms, "roofline_frac": units_per_gpu_step / (fms * 1e-3) / peak,
+                                       "E[X]": runs[-1].mean, "std_error": runs[-1].std_error,
+                                       "note": "BASELINE configs[1] is FE with the |.| floor vs the (.)+ floor: the headline is "
+                                               "the reference's floor (|.|, the only one it codes), this is the other"}
+            except Exception as ex:  # noqa: BLE001
+                line["other_floor"] = {"error": str(ex)[:200]}
             try:                                  # the opt-in dense-draw stream, same workload, for the record
                 with E.Engine(NTPB=512, NB=n_per_gpu // 512, N=N, rng=E.RNG_PHILOX_DENSE, device=local_rank,
                               floor=E.FLOOR_ABS if args.floor == "abs" else E.FLOOR_PLUS, **README) as de:

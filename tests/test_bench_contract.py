@@ -76,3 +76,4 @@ def test_sub_records_em_and_c5_strong():
         assert c5[m]["unit"] == u and c5[m]["value"] > 0 and c5[m]["gpu_launches"] == 3
         assert abs(c5[m]["result"]["E[X]"] - 0.1197325) < 5 * c5[m]["result"]["std_error"] + 2e-4
     assert d["roofline"]["traffic_source"].startswith("static")
+    assert d["other_floor"]["floor"] == "plus" and d["other_floor"]["value"] > 0
