@@ -18,6 +18,8 @@ allreduce of the two FP64 moments per step when N>1.
 BASELINE.json's metric has a second half and a second workload, carried as sub-records of the same line at every N:
   em         configs[2]: EM exact scheme, N=1000, 2^22 paths per GPU (weak): paths/s, ms_per_step, roofline, e2e
   c5_strong  configs[4]: FE and EM at 2^30 GLOBAL paths sharded over the N ranks (strong scaling), 3 steps each
+  c4_sweep   configs[3]: the 20^3 (kappa, theta, sigma) grid with the reference's skip filter (7778 points), 2^20 GLOBAL
+             paths per point sharded over the N ranks, ONE launch per method + one allreduce of 2 x 7778 moments
   other_floor (N=1)  configs[1] names both variance floors: the (.)+ floor on the headline workload
   group_check (N>1)  the single-process group front end (nmch_group_*: ncclCommInitAll, what the C++ classes and
              `--gpus` use) over the same N devices, run by rank 0 after the timed regions: its sums against the
@@ -268,6 +270,8 @@ def main():
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--no-sub-records", action="store_true", help="skip the em / c5_strong / group_check sub-records")
     ap.add_argument("--c5-log2-paths", type=int, default=30, help="GLOBAL paths of the c5_strong sub-record")
+    ap.add_argument("--c4-log2-paths", type=int, default=20, help="GLOBAL paths per grid point of the c4_sweep sub-record")
+    ap.add_argument("--c4-points", type=int, default=20, help="grid points per axis of the c4_sweep sub-record")
     ap.add_argument("--cpu-budget-s", type=float, default=None, help="seconds of host work per CPU-baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -404,6 +408,42 @@ def main():
         sh.close()
         return out
 
+    def sweep(method, n_global, points_per_axis):
+        """BASELINE configs[3]: the (kappa, theta, sigma) grid of src/NMCH/test/exploration.cu:46-52 at `points_per_axis`
+        points per axis (computed in double, then cast), the reference's skip filter 20 k theta < sigma^2 applied
+        (exploration.cu:76), every point on n_global paths sharded over the ranks: ONE launch + ONE allreduce."""
+        import numpy as np
+        P = points_per_axis
+        ax = lambda lo, hi: [np.float32(lo + i * (hi - lo) / (P - 1)) if P > 1 else np.float32(lo) for i in range(P)]  # noqa: E731
+        pts = [(k_, t_, s_) for s_ in ax(0.1, 1.0) for t_ in ax(0.01, 0.5) for k_ in ax(0.1, 10.0)
+               if not (np.float32(20) * k_ * t_ < s_ * s_)]
+        k_, t_, s_ = (np.array(x, np.float32) for x in zip(*pts))
+        sh = ShardedEngine(rank=rank, world=world, device=local_rank, NTPB=512, NB=n_global // 512, N=N,
+                           method=E.METHOD_FE if method == "fe" else E.METHOD_EM, rng=E.RNG_PHILOX, **README)
+        sh.init(1234)
+        sh.explore(k_[:4], t_[:4], s_[:4])                       # warm-up (also sizes nothing: buffers grow below)
+        buf = sh._buffer(len(k_))
+        barrier()
+        l0 = sh.engine.launch_info()["kernel_launches"]
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        sh.engine.explore_async(stream.cuda_stream, k_, t_, s_, buf.data_ptr())
+        from nmch_b200.distributed import allreduce_moments
+        allreduce_moments(buf, None)
+        ev1.record(stream)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = sh.engine.launch_info()["kernel_launches"] - l0
+        sums = buf.cpu().numpy().reshape(-1, 2)
+        sh.close()
+        means = sums[:, 0] / n_global
+        units = len(k_) * n_global * (N if method == "fe" else 1)
+        i0 = int(np.argmin(np.abs(k_ - 0.5) + np.abs(t_ - 0.1) * 10 + np.abs(s_ - 0.3) * 3))
+        return {"points": len(k_), "paths_per_point": n_global, "launch_ms": ms, "gpu_launches": int(launches),
+                "value": units / (ms * 1e-3), "unit": names(method)[1],
+                "all_finite": bool(np.isfinite(sums).all()), "mean_of_E[X]": float(means.mean()),
+                "nearest_to_README_point": {"k": float(k_[i0]), "theta": float(t_[i0]), "sigma": float(s_[i0]), "E[X]": float(means[i0])}}
+
     def stats(result, n_total):
         mean = float(result[0]) / n_total
         var = float(result[1]) / n_total - mean * mean
@@ -457,6 +497,7 @@ def main():
         for m in ("fe", "em"):
             c5[m] = measure(m, c5_n, 3, 1, want_e2e=False)
         sub["c5"] = (c5_n, c5)
+        sub["c4"] = {m: sweep(m, 1 << args.c4_log2_paths, args.c4_points) for m in ("fe", "em")}
 
     # ---- single-process group over the same devices (rank 0, everyone else parked on the host)
     group_check = None
@@ -531,6 +572,11 @@ def main():
                        "gpu_launches": c5["fe"]["launches"], "result": stats(c5["fe"]["result"], c5_n)},
                 "em": {"ms_per_step": c5["em"]["ms_per_step"], "value": c5["em"]["value"], "unit": "paths/s",
                        "gpu_launches": c5["em"]["launches"], "result": stats(c5["em"]["result"], c5_n)}}
+        if "c4" in sub:
+            line["c4_sweep"] = {"workload": f"BASELINE configs[3]: {args.c4_points}^3 grid over kappa in [0.1,10], theta in [0.01,0.5], "
+                                            f"sigma in [0.1,1] with the reference's skip filter, 2^{args.c4_log2_paths} GLOBAL paths per "
+                                            f"point, N={N}, one launch per method, sharded over {world} rank(s)",
+                                "scaling": "strong", "fe": sub["c4"]["fe"], "em": sub["c4"]["em"]}
         if group_check is not None:
             line["group_check"] = group_check
         if world == 1 and args.method == "fe" and args.rng == "philox" and not args.no_sub_records:

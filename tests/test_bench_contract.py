@@ -63,7 +63,8 @@ def test_reference_arm_uses_every_host_thread_under_torchrun_env():
 
 @pytest.mark.gpu
 def test_sub_records_em_and_c5_strong():
-    d = _run("--steps", "3", "--warmup", "3", "--log2-paths", "20", "--c5-log2-paths", "22", "--no-cpu-baseline", "--no-reference-cuda")
+    d = _run("--steps", "3", "--warmup", "3", "--log2-paths", "20", "--c5-log2-paths", "22", "--c4-log2-paths", "14", "--c4-points", "6",
+             "--no-cpu-baseline", "--no-reference-cuda")
     assert d["metric"] == "fe_path_steps_per_s" and d["gpu_launches"] == 3
     em = d["em"]
     assert em["metric"] == "em_paths_per_s" and em["unit"] == "paths/s" and em["value"] > 0 and em["gpu_launches"] == em["steps"]
@@ -77,3 +78,6 @@ def test_sub_records_em_and_c5_strong():
         assert abs(c5[m]["result"]["E[X]"] - 0.1197325) < 5 * c5[m]["result"]["std_error"] + 2e-4
     assert d["roofline"]["traffic_source"].startswith("static")
     assert d["other_floor"]["floor"] == "plus" and d["other_floor"]["value"] > 0
+    c4 = d["c4_sweep"]
+    for m in ("fe", "em"):
+        assert c4[m]["gpu_launches"] == 1 and c4[m]["all_finite"] and c4[m]["points"] == 200 and c4[m]["launch_ms"] > 0
