@@ -61,6 +61,10 @@ public:
        K = S_0, NMCH.cu:7).  Outputs (each n_strikes long, may be null): E[(S_T-K)^+], E[((S_T-K)^+)^2], delta.
        Returns the launch time in ms. */
     float compute_strikes(int n_strikes, const float *strikes, float *price_out, float *price_squared_out, float *delta_out);
+    /* The same with the pathwise vega d E[(S_T-K)^+] / d v_0 and its standard error (FE on the native Philox stream
+       only: the tangent rides the native Euler step; any other method / stream fails like every engine error). */
+    float compute_greeks(int n_strikes, const float *strikes, float *price_out, float *price_squared_out, float *delta_out,
+                         float *vega_out, float *vega_err_out);
 
     virtual ~NMCH();
 

@@ -128,6 +128,27 @@ int nmch_engine_compute_strikes(nmch_engine_t *e, const float *strikes, int n_st
 /* stream form: 4*n_strikes raw sums {payoff, payoff^2, delta, itm} per strike into DEVICE memory, no host sync */
 int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const float *strikes, int n_strikes,
                                       double *d_moments);
+/* ---- ... and the pathwise vega (the second half of SURVEY.md §8f rank 2, "pathwise delta/vega"; no reference
+ * equivalent).  FE on the native Philox stream only: one pass of the native step (the same words and instructions, so
+ * the same S_T, as compute()) carries every path's tangent dS_T/dv_0 in registers; the fold then adds, per strike,
+ * vega = 1{S_T > K} dS_T/dv_0 -- the sensitivity of the undiscounted price E[(S_T - K)^+] to the initial variance v_0
+ * (the reference reports undiscounted prices too, NMCH_FE.cu:171-175) -- and its square for the standard error.
+ * Other methods / stream modes return NMCH_ERR_ARG.  Streams advance exactly as for compute(). */
+typedef struct {
+    float  strike;
+    double sum_payoff;        /* sum (S_T - K)^+                      */
+    double sum_payoff_sq;     /* sum ((S_T - K)^+)^2                  */
+    double sum_delta;         /* sum 1{S_T > K} S_T / S_0             */
+    double sum_itm;           /* sum 1{S_T > K}                       */
+    double sum_vega;          /* sum 1{S_T > K} dS_T/dv_0   (pathwise d payoff / d v_0) */
+    double sum_vega_sq;       /* sum (1{S_T > K} dS_T/dv_0)^2         */
+    unsigned long long n_paths;
+    float  exec_ms;
+} nmch_greek_moments_t;
+int nmch_engine_compute_greeks(nmch_engine_t *e, const float *strikes, int n_strikes, nmch_greek_moments_t *out);
+/* stream form: 6*n_strikes raw sums {payoff, payoff^2, delta, itm, vega, vega^2} per strike into DEVICE memory */
+int nmch_engine_compute_greeks_async(nmch_engine_t *e, void *cuda_stream, const float *strikes, int n_strikes,
+                                     double *d_moments);
 
 /* finalize() (NMCH_FE.cu:326-331); idempotent here (the reference double-frees) */
 int nmch_engine_finalize(nmch_engine_t *e);
@@ -168,6 +189,7 @@ int nmch_group_explore(nmch_group_t *g, const float *k, const float *theta, cons
 int nmch_group_finalize(nmch_group_t *g);
 void nmch_group_destroy(nmch_group_t *g);
 int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_strikes, nmch_strike_moments_t *out);
+int nmch_group_compute_greeks(nmch_group_t *g, const float *strikes, int n_strikes, nmch_greek_moments_t *out);
 float nmch_group_init_ms(const nmch_group_t *g);
 int nmch_group_size(const nmch_group_t *g);
 

@@ -717,6 +717,77 @@ int nmch_engine_compute_strikes_async(nmch_engine_t *e, void *cuda_stream, const
     return strikes_launch(e, static_cast<cudaStream_t>(cuda_stream), strikes, n_strikes, d_moments);
 }
 
+// ---- strike vector with pathwise delta and vega (FE, native Philox stream) ------------------------------------------
+static int greeks_launch(nmch_engine *e, cudaStream_t stream, const float *strikes, int n_strikes, double *d_out6)
+{
+    const nmch_params_t &p = e->p;
+    if (p.method != NMCH_METHOD_FE || p.rng != NMCH_RNG_PHILOX)
+        return fail(NMCH_ERR_ARG, "compute_greeks: the pathwise tangent is carried by the native FE step (method FE, rng PHILOX)");
+    int rc = ensure_sv(e, (size_t)e->n_local);
+    if (rc) return rc;
+    if ((size_t)e->n_local > e->t_cap) {
+        engine_dev_free(e, e->d_T);
+        e->d_T = nullptr;
+        e->t_cap = 0;
+        CU_TRY(engine_dev_malloc(e, (void **)&e->d_T, (size_t)e->n_local * sizeof(float), "dS_T/dv_0"));
+        e->t_cap = (size_t)e->n_local;
+    }
+    // reduction slots: 0 = the path kernel's own K = S_0 moments, 1 + 3j .. 3 + 3j = strike j (payoff, delta, vega)
+    const size_t slots = 1 + 3 * (size_t)n_strikes;
+    rc = ensure_buffers(e, slots, (size_t)greek_blocks_per_slot(), (size_t)n_strikes * sizeof(float));
+    if (rc) return rc;
+    const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
+    if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
+    rc = ensure_buffers(e, 1, (size_t)bpp, 0);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(e->d_points, strikes, (size_t)n_strikes * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaStreamSynchronize(stream));                     // `strikes` is caller memory of unknown lifetime
+    FeLaunch L;
+    fill_fe_launch(e, L, 1, (int)bpp, 1);
+    ReduceBuffers rb0{e->d_partials, e->d_tickets, e->h_out_dev};
+    CU_TRY(launch_fe_tangent(L, p.floor, rb0, e->d_S, e->d_V, e->d_T, stream, &e->kinfo));
+    e->draw_offset += 2ull * (unsigned long long)p.N;          // the stream advances like one compute()
+    // same stream: the path kernel (and its use of the partial buffer) is complete before the fold starts
+    ReduceBuffers rb{e->d_partials, e->d_tickets + 1, d_out6};
+    CU_TRY(launch_strike_greeks(e->d_S, e->d_T, e->n_local, static_cast<const float *>(e->d_points), n_strikes, p.S_0, rb, stream));
+    e->launches += 2;
+    return NMCH_OK;
+}
+
+int nmch_engine_compute_greeks(nmch_engine_t *e, const float *strikes, int n_strikes, nmch_greek_moments_t *out)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!strikes || !out || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return fail(NMCH_ERR_ARG, "bad strike arguments");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    rc = ensure_buffers(e, 1 + 3 * (size_t)n_strikes, 1, 0);   // host-visible result buffer large enough
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = greeks_launch(e, e->stream, strikes, n_strikes, e->h_out_dev + 2);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev1, e->stream));
+    CU_TRY(cudaEventSynchronize(e->ev1));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    for (int j = 0; j < n_strikes; ++j) {
+        const double *m = e->h_out + 2 + 6 * (size_t)j;
+        out[j] = nmch_greek_moments_t{strikes[j], m[0], m[1], m[2], m[3], m[4], m[5], e->n_local, ms};
+    }
+    return engine_check_guards(e);
+}
+
+int nmch_engine_compute_greeks_async(nmch_engine_t *e, void *cuda_stream, const float *strikes, int n_strikes,
+                                     double *d_moments)
+{
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (!strikes || !d_moments || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return fail(NMCH_ERR_ARG, "bad strike arguments");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(NMCH_ERR_CUDA, "cudaSetDevice failed");
+    return greeks_launch(e, static_cast<cudaStream_t>(cuda_stream), strikes, n_strikes, d_moments);
+}
+
 int nmch_engine_finalize(nmch_engine_t *e)
 {
     if (!e) return fail(NMCH_ERR_ARG, "null engine");
@@ -730,6 +801,7 @@ int nmch_engine_finalize(nmch_engine_t *e)
     engine_dev_free(e, e->d_points);
     engine_dev_free(e, e->d_S);
     engine_dev_free(e, e->d_V);
+    engine_dev_free(e, e->d_T);
     engine_dev_free(e, e->xs.d);
     engine_dev_free(e, e->xs.bm_flag);
     engine_dev_free(e, e->xs.bm_extra);
@@ -749,6 +821,7 @@ int nmch_engine_finalize(nmch_engine_t *e)
     e->h_out = e->h_out_dev = nullptr; e->out_cap = 0;
     e->d_points = nullptr; e->points_cap = 0;
     e->d_S = e->d_V = nullptr; e->sv_cap = 0;
+    e->d_T = nullptr; e->t_cap = 0;
     e->xs = XorwowState{};
     e->xtab = nullptr;
     e->ev0 = e->ev1 = nullptr;

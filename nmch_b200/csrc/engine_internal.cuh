@@ -39,6 +39,8 @@ struct nmch_engine {
     size_t points_cap = 0;
     float *d_S = nullptr, *d_V = nullptr;    // parity hook buffers
     size_t sv_cap = 0;
+    float *d_T = nullptr;                    // dS_T/dv_0 of every local path (compute_greeks)
+    size_t t_cap = 0;
     // XORWOW-compat state
     nmchb::XorwowSkipTables *xtab = nullptr;
     nmchb::XorwowState xs{};

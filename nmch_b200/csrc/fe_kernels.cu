@@ -14,6 +14,7 @@
 //   * S' = S + S * (r dt + q sin * zr + q cos * zc),  V' = g(V*va + vb + q sin * vs)
 //   state (S, V, counters) stays in registers for all N steps: zero HBM traffic in the loop.
 #include "compat_math.cuh"
+#include "fe_step.cuh"
 #include "kernels.cuh"
 #include "xorwow_device.cuh"
 
@@ -22,40 +23,6 @@ namespace nmchb {
 // ------------------------------------------------------------------------------------------
 // native Philox kernel
 // ------------------------------------------------------------------------------------------
-// PRECISE_V: V' = g(V - kdt*V + (vb + q sin * vs)) with the product rounded once, instead of the folded
-// V*va + vb + ... -- one more FP32 operation.  The folded va = 1 - k*dt carries a rounding error of up to 3e-8, i.e. a
-// relative error of up to 3e-8 / (k dt) in the mean-reversion speed; fold_fe_point compensates vb so that the
-// long-run level stays theta, which is all the 3-standard-error modes need.  The XORWOW_FAST mode promises 1e-5
-// against the reference on identical draws and takes the exact form.
-template <int FLOOR, bool PRECISE_V = false>
-__device__ __forceinline__ void fe_step_native(float &S, float &V, uint32_t wa, uint32_t wb, float rdt,
-                                               float zr, float zc, const FePoint &pc)
-{
-    // uniforms as cuRAND forms them (curand_uniform.h:69-72, curand_normal.h:72-75): u = x 2^-32 + 2^-33 in (0, 1],
-    // angle = y (2 pi 2^-32) -- an integer-to-float conversion (I2FP) and one FFMA / FMUL.  Against bit
-    // splicing ((w >> 9) | 0x3f800000, then a subtraction) this costs the same instruction count, but I2FP issues beside
-    // the FP32 work where LEA.HI does not (profiles/r02_pipe_rates2.txt: -1 % on the kernel), and the native mode now
-    // feeds the same uniforms as the draw-compatible modes into its fast transforms.
-    constexpr float k2Pow32Inv = 2.3283064e-10f, k2Pow32Inv2Pi = 2.3283064e-10f * 6.2831855f;
-    const float u = fmaf(__uint2float_rn(wa), k2Pow32Inv, k2Pow32Inv * 0.5f);
-    const float l2 = lg2_approx(u);                   // <= 0
-    const float q = sqrt_approx(-(V * l2));           // sqrt(V) * sqrt(-lg2 u)
-    const float ang = __uint2float_rn(wb) * k2Pow32Inv2Pi;   // cuRAND adds half a step (7e-10 rad, below the angle's ulp)
-    const float gs = q * sin_approx(ang);
-    const float gc = q * cos_approx(ang);
-    float m = fmaf(gs, zr, rdt);                      // relative increment; S' = S + S*m keeps r*dt at full precision
-    m = fmaf(gc, zc, m);                              // (a folded 1 + r*dt would round by up to 6e-8 every step, a
-    S = fmaf(S, m, S);                                //  systematic drift of N * 6e-8 on S_T)
-    float vn;
-    if constexpr (PRECISE_V) {
-        vn = fmaf(-pc.kdt, V, V) + fmaf(gs, pc.vs, pc.vb);
-    } else {
-        vn = fmaf(V, pc.va, pc.vb);
-        vn = fmaf(gs, pc.vs, vn);
-    }
-    V = (FLOOR == kFloorAbs) ? fabsf(vn) : fmaxf(vn, 0.0f);
-}
-
 // One step in either arithmetic: the fused fast-math step above, or (EXACT) cuRAND's IEEE Box-Muller and the
 // reference's pinned update on the same two Philox words -- the Philox-compatible validation mode, which thereby
 // shares the counter hoisting, the tiling and the several-paths-per-thread structure of the product kernel.

@@ -265,23 +265,26 @@ int nmch_group_explore(nmch_group_t *g, const float *k, const float *theta, cons
     return run_points(g, k, theta, sigma, n_points, out);
 }
 
-int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_strikes, nmch_strike_moments_t *out)
+// per strike `per` doubles of raw sums: 4 (payoff, payoff^2, delta, itm) or 6 (+ vega, vega^2; FE native stream only)
+static int group_strikes_impl(nmch_group_t *g, const float *strikes, int n_strikes, int per, float *ms_out)
 {
     if (!g || !g->inited) return engine_fail(NMCH_ERR_STATE, "group not initialised");
-    if (!strikes || !out || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return engine_fail(NMCH_ERR_ARG, "bad strike arguments");
+    if (!strikes || n_strikes <= 0 || n_strikes > NMCH_MAX_STRIKES) return engine_fail(NMCH_ERR_ARG, "bad strike arguments");
     DeviceRestore restore;
-    int rc = ensure_moments(g, 2 * (size_t)n_strikes);          // 4 doubles per strike
+    const size_t count = (size_t)per * (size_t)n_strikes;
+    int rc = ensure_moments(g, (count + 1) / 2);               // ensure_moments counts pairs of doubles
     if (rc) return rc;
     for (int i = 0; i < g->n; ++i) {
         GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
         GROUP_CU_TRY(cudaEventRecord(g->ev0[i], g->stream[i]));
-        rc = nmch_engine_compute_strikes_async(g->eng[i], g->stream[i], strikes, n_strikes, g->d_mom[i]);
+        rc = per == 6 ? nmch_engine_compute_greeks_async(g->eng[i], g->stream[i], strikes, n_strikes, g->d_mom[i])
+                      : nmch_engine_compute_strikes_async(g->eng[i], g->stream[i], strikes, n_strikes, g->d_mom[i]);
         if (rc) return rc;
     }
     if (g->n > 1) {
         ncclResult_t r = g_nccl.GroupStart();
         for (int i = 0; i < g->n && r == ncclSuccess; ++i)
-            r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], 4 * (size_t)n_strikes, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
+            r = g_nccl.AllReduce(g->d_mom[i], g->d_mom[i], count, ncclDouble, ncclSum, g->comm[i], g->stream[i]);
         if (r == ncclSuccess) r = g_nccl.GroupEnd();
         if (r != ncclSuccess) return nccl_fail("strike allreduce", r);
     }
@@ -289,7 +292,7 @@ int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_stri
     for (int i = 0; i < g->n; ++i) {
         GROUP_CU_TRY(cudaSetDevice(g->dev[i]));
         if (i == 0)
-            GROUP_CU_TRY(cudaMemcpyAsync(g->h_mom, g->d_mom[0], 4 * (size_t)n_strikes * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]));
+            GROUP_CU_TRY(cudaMemcpyAsync(g->h_mom, g->d_mom[0], count * sizeof(double), cudaMemcpyDeviceToHost, g->stream[0]));
         GROUP_CU_TRY(cudaEventRecord(g->ev1[i], g->stream[i]));
     }
     for (int i = 0; i < g->n; ++i) {
@@ -300,9 +303,32 @@ int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_stri
         GROUP_CU_TRY(cudaEventElapsedTime(&t, g->ev0[i], g->ev1[i]));
         if (t > ms) ms = t;
     }
+    *ms_out = ms;
+    return NMCH_OK;
+}
+
+int nmch_group_compute_strikes(nmch_group_t *g, const float *strikes, int n_strikes, nmch_strike_moments_t *out)
+{
+    if (!out) return engine_fail(NMCH_ERR_ARG, "bad strike arguments");
+    float ms = 0.0f;
+    const int rc = group_strikes_impl(g, strikes, n_strikes, 4, &ms);
+    if (rc) return rc;
     for (int j = 0; j < n_strikes; ++j) {
         const double *m = g->h_mom + 4 * (size_t)j;
         out[j] = nmch_strike_moments_t{strikes[j], m[0], m[1], m[2], m[3], g->n_paths, ms};
+    }
+    return NMCH_OK;
+}
+
+int nmch_group_compute_greeks(nmch_group_t *g, const float *strikes, int n_strikes, nmch_greek_moments_t *out)
+{
+    if (!out) return engine_fail(NMCH_ERR_ARG, "bad strike arguments");
+    float ms = 0.0f;
+    const int rc = group_strikes_impl(g, strikes, n_strikes, 6, &ms);
+    if (rc) return rc;
+    for (int j = 0; j < n_strikes; ++j) {
+        const double *m = g->h_mom + 6 * (size_t)j;
+        out[j] = nmch_greek_moments_t{strikes[j], m[0], m[1], m[2], m[3], m[4], m[5], g->n_paths, ms};
     }
     return NMCH_OK;
 }

@@ -90,6 +90,14 @@ cudaError_t launch_strike_moments(const float *d_S, unsigned long long n_local, 
                                   float S0, ReduceBuffers rb, cudaStream_t stream);
 int strike_blocks_per_slot();
 
+// greeks_kernels.cu: native FE pass carrying the pathwise tangent in v_0 (leaves S_T, V_T, dS_T/dv_0 on the device), and
+// the per-strike fold of payoff / delta / vega: 3 reduction slots = 6 doubles per strike
+cudaError_t launch_fe_tangent(const FeLaunch &L, int floor_kind, ReduceBuffers rb, float *S_out, float *V_out, float *B_out,
+                              cudaStream_t stream, KernelInfo *info);
+cudaError_t launch_strike_greeks(const float *d_S, const float *d_B, unsigned long long n_local, const float *d_strikes,
+                                 int n_strikes, float S0, ReduceBuffers rb, cudaStream_t stream);
+int greek_blocks_per_slot();
+
 // xorwow.cu
 struct XorwowSkipTables;                // device tables M_m^q, q = 1..3, m = 0..31
 cudaError_t xorwow_tables_create(XorwowSkipTables **out);

@@ -45,6 +45,20 @@ class Moments:
                        self.n_paths + other.n_paths, max(self.exec_ms, other.exec_ms))
 
 
+
+def _greek_rows(out):
+    """Per strike: payoff moments, pathwise delta, in-the-money share, pathwise vega (d price / d v_0) and its
+    standard error."""
+    rows = []
+    for m in out:
+        n = m.n_paths
+        vega = m.sum_vega / n
+        var = max(m.sum_vega_sq / n - vega * vega, 0.0)
+        rows.append({"strike": m.strike, "moments": Moments(m.sum_payoff, m.sum_payoff_sq, n, m.exec_ms),
+                     "delta": m.sum_delta / n, "itm": m.sum_itm / n, "vega_v0": vega,
+                     "vega_v0_se": (var / max(n - 1, 1)) ** 0.5})
+    return rows
+
 class Engine:
     def __init__(self, NTPB=512, NB=512, T=1.0, S_0=1.0, v_0=0.1, r=0.0, k=0.5, rho=-0.7, theta=0.1, sigma=0.3,
                  N=1000, method=METHOD_FE, floor=FLOOR_ABS, rng=RNG_PHILOX, device=-1, n_paths=0, first_path=0,
@@ -118,6 +132,14 @@ class Engine:
                                                          len(strikes), out))
         return [{"strike": m.strike, "moments": Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms),
                  "delta": m.sum_delta / m.n_paths, "itm": m.sum_itm / m.n_paths} for m in out]
+
+    def compute_greeks(self, strikes):
+        """compute_strikes() plus the pathwise vega d E[(S_T - K)^+] / d v_0 (FE, native Philox stream only)."""
+        strikes = np.ascontiguousarray(strikes, np.float32)
+        out = (capi.NmchGreekMoments * len(strikes))()
+        capi.check(self._lib.nmch_engine_compute_greeks(self._h, strikes.ctypes.data_as(C.POINTER(C.c_float)),
+                                                        len(strikes), out))
+        return _greek_rows(out)
 
     def check(self) -> None:
         """Synchronise and, in the checked build, sweep the guard bands / surface a failed device assert."""
@@ -198,6 +220,13 @@ class Group:
                                                         len(strikes), out))
         return [{"strike": m.strike, "moments": Moments(m.sum_payoff, m.sum_payoff_sq, m.n_paths, m.exec_ms),
                  "delta": m.sum_delta / m.n_paths, "itm": m.sum_itm / m.n_paths} for m in out]
+
+    def compute_greeks(self, strikes):
+        strikes = np.ascontiguousarray(strikes, np.float32)
+        out = (capi.NmchGreekMoments * len(strikes))()
+        capi.check(self._lib.nmch_group_compute_greeks(self._h, strikes.ctypes.data_as(C.POINTER(C.c_float)),
+                                                       len(strikes), out))
+        return _greek_rows(out)
 
     @property
     def size(self) -> int:

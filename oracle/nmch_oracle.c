@@ -600,6 +600,53 @@ static void fe_run_impl(const orc_params_t *p, int rng_kind, int floor_kind, uin
     if (sumsq) *sumsq = acc2;
 }
 
+/* FE with the pathwise tangent in v_0 (checker of the product's compute_greeks; the reference has no
+ * sensitivities).  (S, V) advance by the reference's step (NMCH_FE.cu:156-163, fe_step above); the tangent
+ * A = dV/dv_0, B = dS/dv_0 is that step differentiated by hand and carried in DOUBLE, so that the checker does not
+ * share the rounding of the float tangent it checks:
+ *   sv = sqrt(V), z = rho gx + sqrt(1-rho^2) gy, h = A / (2 sv)
+ *   B' = B (1 + r dt + sv sqrt(dt) z) + S sqrt(dt) z h
+ *   A'' = A (1 - k dt) + sigma sqrt(dt) gx h,   A' = sign(V'') A'' for |.|,  1{V'' > 0} A'' for (.)+
+ * V = 0 (only the (.)+ floor parks paths there, with A = 0 from the parking step on) takes h = 0. */
+void orc_fe_tangent_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,
+                        uint64_t first_path, uint64_t n_paths, float *S_out, float *V_out, double *B_out, int threads)
+{
+    const float dt = p->T / p->N;
+    const float sqrt_dt = sqrtf(dt);
+    const float sqrt_rho = sqrtf(1 - p->rho * p->rho);
+    xorwow_build_matrices();
+    if (threads <= 0) threads = orc_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(threads) schedule(static)
+#endif
+    for (int64_t i = 0; i < (int64_t)n_paths; ++i) {
+        orc_rng_t st;
+        orc_rng_init(&st, rng_kind, seed, first_path + (uint64_t)i, 0);
+        float St = p->S_0, Vt = p->v_0;
+        double A = 1.0, B = 0.0;
+        for (int n = 0; n < p->N; ++n) {
+            float gx, gy;
+            orc_normal2(&st, &gx, &gy);
+            const double sv = sqrt((double)Vt);
+            const double z = (double)p->rho * gx + (double)sqrt_rho * gy;
+            const double h = Vt > 0.0f ? A / (2.0 * sv) : 0.0;
+            const double Bn = B * (1.0 + (double)p->r * dt + sv * sqrt_dt * z) + (double)St * sqrt_dt * z * h;
+            const double An = A * (1.0 - (double)p->k * dt) + (double)p->sigma * sqrt_dt * gx * h;
+            /* the sign of the pre-floor variance, from the same float expression the step evaluates */
+            float c = p->theta - Vt;   c = c * p->k;   c = fmaf(c, dt, Vt);
+            float e = sqrtf(Vt) * p->sigma;   e = e * sqrt_dt;
+            const float Vpre = fmaf(gx, e, c);
+            fe_step(&St, &Vt, gx, gy, p->r, p->k, p->rho, p->theta, p->sigma, dt, sqrt_dt, sqrt_rho, floor_kind);
+            B = Bn;
+            if (floor_kind == ORC_FLOOR_ABS) A = Vpre < 0.0f ? -An : An;
+            else A = Vpre > 0.0f ? An : 0.0;
+        }
+        if (S_out) S_out[i] = St;
+        if (V_out) V_out[i] = Vt;
+        if (B_out) B_out[i] = B;
+    }
+}
+
 /* The exploration sweep (exploration.cu:71-88): one set_* + compute() per point on CONTINUED
  * per-path streams; sums[2*i], sums[2*i+1] = raw payoff moments of point i. */
 void orc_fe_sweep(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,

@@ -85,6 +85,11 @@ void orc_fe_run_at(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t
                    uint64_t first_path, uint64_t n_paths, int calls,
                    float *S_out, float *V_out, double *sum, double *sumsq, int threads);
 
+/* FE paths with the pathwise tangent dS_T/dv_0 (double) -- the checker of nmch_engine_compute_greeks; the step is
+ * NMCH_FE.cu:156-163, its derivative is new (the reference has no sensitivities). */
+void orc_fe_tangent_run(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,
+                        uint64_t first_path, uint64_t n_paths, float *S_out, float *V_out, double *B_out, int threads);
+
 /* The exploration sweep (src/NMCH/test/exploration.cu:71-88): per point set_k/theta/sigma + compute()
  * on continued streams.  sums has 2*n_points entries (raw sum, raw sum of squares per point). */
 void orc_fe_sweep(const orc_params_t *p, int rng_kind, int floor_kind, uint64_t seed,

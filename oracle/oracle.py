@@ -188,6 +188,20 @@ def fe_run_at(p: Params, offset, rng=RNG_PHILOX, floor=FLOOR_ABS, seed=1234, fir
     return _run(lib().orc_fe_run_at, p, (rng, floor, seed, offset), first_path, n_paths, calls, want_paths, threads)
 
 
+def fe_tangent_run(p: Params, rng=RNG_PHILOX, floor=FLOOR_ABS, seed=1234, first_path=0, n_paths=1024, threads=0):
+    """FE paths with the pathwise tangent dS_T/dv_0 (checker of compute_greeks): returns S, V (float32), B (float64)."""
+    S = np.empty(n_paths, np.float32)
+    V = np.empty(n_paths, np.float32)
+    B = np.empty(n_paths, np.float64)
+    cp = p.c()
+    fn = lib().orc_fe_tangent_run
+    fn.restype = None
+    fn.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
+                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]
+    fn(C.byref(cp), rng, floor, seed, first_path, n_paths, _fp(S, C.c_float), _fp(V, C.c_float), _fp(B, C.c_double), threads)
+    return {"S": S, "V": V, "B": B}
+
+
 def fe_sweep(p: Params, k, theta, sigma, rng=RNG_XORWOW, floor=FLOOR_ABS, seed=1234, first_path=0, n_paths=1024,
              threads=0):
     """exploration.cu:71-88 for FE: returns an (n_points, 2) array of raw payoff sums."""

@@ -137,6 +137,27 @@ float NMCH<rnd_state>::compute_strikes(int n_strikes, const float *strikes, floa
 }
 
 template <typename rnd_state>
+float NMCH<rnd_state>::compute_greeks(int n_strikes, const float *strikes, float *price_out, float *sq_out, float *delta_out,
+                                      float *vega_out, float *vega_err_out)
+{
+    if (!group) testNMCH(NMCH_ERR_STATE);
+    testNMCH(nmch_group_set_params(group, k, theta, sigma));
+    std::vector<nmch_greek_moments_t> m((size_t)(n_strikes > 0 ? n_strikes : 0));
+    testNMCH(nmch_group_compute_greeks(group, strikes, n_strikes, m.data()));
+    for (int j = 0; j < n_strikes; ++j) {
+        const double n = (double)m[j].n_paths;
+        const double vega = m[j].sum_vega / n;
+        const double var = m[j].sum_vega_sq / n - vega * vega;
+        if (price_out) price_out[j] = (float)(m[j].sum_payoff / n);
+        if (sq_out) sq_out[j] = (float)(m[j].sum_payoff_sq / n);
+        if (delta_out) delta_out[j] = (float)(m[j].sum_delta / n);
+        if (vega_out) vega_out[j] = (float)vega;
+        if (vega_err_out) vega_err_out[j] = (float)std::sqrt((var > 0.0 ? var : 0.0) / (n > 1.0 ? n - 1.0 : 1.0));
+    }
+    return n_strikes > 0 ? m[0].exec_ms : 0.0f;
+}
+
+template <typename rnd_state>
 void NMCH<rnd_state>::apply_legacy_k1_moment()
 {
     // reference FE_k1 / EM_k1: SR = payoff / n; VR = SR * SR / n; price_squared = sum VR = (sum payoff^2) / n^3

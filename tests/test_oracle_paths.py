@@ -154,3 +154,23 @@ def test_native_em_restatement_is_statistically_exact(kw):
     # a second call is a different stream
     r2 = o.em_native_run(p, seed=99, n_paths=1024, call=1, want_paths=True)
     assert not np.array_equal(r2["S"], r["S"][:1024])
+
+
+def test_tangent_oracle_agrees_with_bump_and_revalue_on_the_same_draws():
+    """orc_fe_tangent_run (checker of compute_greeks): the pathwise vega estimator 1{S_T > K} dS_T/dv_0 against a
+    central difference of the oracle's own prices in v_0 on the SAME Philox draws, and against the semi-analytic
+    d price / d v_0 within the estimator's standard error plus the Euler bias."""
+    n, N, h = 40000, 100, 1e-3
+    for floor, kw, bias in [(o.FLOOR_ABS, {}, 0.01), (o.FLOOR_PLUS, dict(k=2.08, theta=0.108, sigma=1.0), 0.03)]:
+        r = o.fe_tangent_run(o.Params(N=N, **kw), floor=floor, n_paths=n)
+        plain = o.fe_run(o.Params(N=N, **kw), rng=o.RNG_PHILOX, floor=floor, n_paths=n, want_paths=True)
+        assert np.array_equal(r["S"], plain["S"]) and np.array_equal(r["V"], plain["V"])   # the tangent does not disturb the paths
+        est = np.where(r["S"] > 1.0, r["B"], 0.0)
+        se = est.std() / np.sqrt(n)
+        up = o.fe_run(o.Params(N=N, v_0=0.1 + h, **kw), rng=o.RNG_PHILOX, floor=floor, n_paths=n)
+        dn = o.fe_run(o.Params(N=N, v_0=0.1 - h, **kw), rng=o.RNG_PHILOX, floor=floor, n_paths=n)
+        bump = (up["mean"] - dn["mean"]) / (2 * h)
+        assert abs(est.mean() - bump) < 1.5 * se + 2e-3, (floor, est.mean(), bump, se)
+        akw = {("kappa" if a == "k" else a): b for a, b in kw.items()}
+        analytic = (o.heston_call(v0=0.1 + h, **akw) - o.heston_call(v0=0.1 - h, **akw)) / (2 * h)
+        assert abs(est.mean() - analytic) < 4 * se + bias, (floor, est.mean(), analytic, se)
