@@ -2,7 +2,7 @@
 (nmch_b200/libnmch_b200_checked.so = the same sources with -DNMCHB_CHECKS: device-side asserts on every index the
 kernels form, guard bands around every device buffer swept after each blocking call) runs the cases where an
 indexing mistake would show: ragged path counts, 64-bit path indices, shards, several tiles per block, many-point
-sweeps, every stream mode and method, the strike pass, the single-process group.  A failed assert or an overwritten
+sweeps, every stream mode and method, the strike and greeks passes, the single-process group.  A failed assert or an overwritten
 guard band comes back as NMCH_ERR_CUDA and fails the case.  The sweep itself is proved by a planted overrun."""
 import json
 import os
@@ -114,6 +114,16 @@ CASES = textwrap.dedent(r"""
                 r = e.compute_strikes(np.linspace(0.7, 1.3, 64))
                 assert len(r) == 64
         case(f"strikes method={method}", run)
+    def greeks():
+        for n, first in ((4096 * 2 + 3, 0), (1, 0), (8192 + 17, (1 << 32) - 4096)):
+            for floor in (0, 1):
+                with E.Engine(NTPB=1, NB=1, N=9, floor=floor, n_paths=(1 << 33) if first else n, first_path=first, n_local=n) as e:
+                    e.init(4)
+                    r = e.compute_greeks(np.linspace(0.7, 1.3, 64))
+                    assert len(r) == 64 and all(np.isfinite(x["vega_v0"]) for x in r)
+                    e.compute_greeks([1.0])
+                    e.compute()
+    case("greeks (tangent pass + fold), ragged and 64-bit shard", greeks)
     def shards():
         n = 3 * 4096 + 100
         whole = None
@@ -133,6 +143,7 @@ CASES = textwrap.dedent(r"""
             g.compute()
             g.explore(grid_k[:4], grid_t[:4], grid_s[:4])
             g.compute_strikes([0.9, 1.0, 1.1])
+            g.compute_greeks([0.9, 1.0, 1.1])
         if L.nmch_device_count() > 1:
             with E.Group(2, NTPB=1, NB=1, N=5, n_paths=4096 * 4 + 11) as g:
                 g.init(8)
