@@ -2,10 +2,12 @@
 # round-2 closing rehearsal of what the driver runs on one GPU: full GPU suite, smoke, reference arm, bench
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+if [ "$1" != bench ]; then
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r02_test_gpu_final.log 2>&1; echo "pytest gpu rc=$?"; tail -4 gpurun_out/r02_test_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?"
-/usr/bin/time -f "ref arm wall %e s" timeout 900 python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; echo "ref arm rc=$?"; tail -1 gpurun_out/r02_bench_reference_arm.err
-/usr/bin/time -f "bench wall %e s" timeout 900 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$?"; tail -1 gpurun_out/r02_bench_1gpu.err
+fi
+t0=$SECONDS; timeout 900 python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; echo "ref arm rc=$? wall $((SECONDS-t0)) s"
+t0=$SECONDS; timeout 900 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$? wall $((SECONDS-t0)) s"
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r02_bench_1gpu.json").read().strip().splitlines()[-1])
