@@ -736,7 +736,8 @@ static int greeks_launch(nmch_engine *e, cudaStream_t stream, const float *strik
     const size_t slots = 1 + 3 * (size_t)n_strikes;
     rc = ensure_buffers(e, slots, (size_t)greek_blocks_per_slot(), (size_t)n_strikes * sizeof(float));
     if (rc) return rc;
-    const unsigned long long bpp = (e->n_local + 255ull) / 256ull;
+    const unsigned long long tile = (unsigned long long)tangent_tile_paths();
+    const unsigned long long bpp = (e->n_local + tile - 1ull) / tile;
     if (bpp == 0 || bpp > 0x7fffffffull) return fail(NMCH_ERR_ARG, "launch grid out of range");
     rc = ensure_buffers(e, 1, (size_t)bpp, 0);
     if (rc) return rc;

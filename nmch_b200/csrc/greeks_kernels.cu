@@ -7,42 +7,97 @@
 //   leaves S_T, V_T and dS_T/dv_0 in HBM (12 bytes per path) and reduces the K = S_0 payoff moments like every path kernel.
 // strike_greeks_kernel: folds the two terminal arrays per strike: payoff moments, delta = 1{S_T > K} S_T / S_0,
 //   vega = 1{S_T > K} dS_T/dv_0 and its square (for the standard error), through the deterministic ticket reduction.
-// Not a throughput path (one path per thread, no hoisting): 2^24 paths x 1000 steps take about twice the plain pass.
 #include "fe_step.cuh"
 #include "kernels.cuh"
 
 namespace nmchb {
 
 constexpr int kTangentThreads = 256;
+constexpr int kTangentPaths = 2;            // paths per thread: the tangent pair doubles the per-path state (52 registers, 32 warps per SM)
+constexpr int kTangentTile = kTangentPaths * kTangentThreads;
 
+// The loop of fe_philox_kernel (fe_kernels.cu) with the tangent step: one tile of kTangentTile paths per block, the
+// Philox counter split where its low word would wrap so that the per-path invariants of rounds 1-2 are hoisted and the
+// path-independent multiplies sit on the uniform datapath; a pass may start on the second half of a block (an odd
+// number of steps before it) and end on a first half.
 template <int FLOOR>
-__global__ void __launch_bounds__(kTangentThreads)
+__global__ void __launch_bounds__(kTangentThreads, 4)
 fe_tangent_kernel(const __grid_constant__ FeLaunch L, ReduceBuffers rb, float *__restrict__ S_out,
                   float *__restrict__ V_out, float *__restrict__ B_out)
 {
-    const unsigned long long idx = (unsigned long long)blockIdx.x * kTangentThreads + threadIdx.x;
-    const bool active = idx < L.n_local;
-    const unsigned long long g = L.first_path + (active ? idx : 0ull);
-    const uint32_t path_lo = (uint32_t)g, path_hi = (uint32_t)(g >> 32);
+    constexpr int P = kTangentPaths;
     NMCHB_ASSERT(blockDim.x == kTangentThreads && (int)blockIdx.x < L.blocks_per_point && L.n_points == 1);
-    float S = L.S0, V = L.v0, A = 1.0f, B = 0.0f;
-    U4 w{0u, 0u, 0u, 0u};
-    for (int n = 0; n < L.N; ++n) {
-        const unsigned long long pos = L.draw_offset + 2ull * (unsigned long long)n;    // u32 words consumed so far
-        const bool second = (pos & 2ull) != 0ull;                                      // second half of its block
-        if (n == 0 || !second) {
-            const unsigned long long blk = pos >> 2;
-            w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo, path_hi, L.keys);
+    NMCHB_ASSERT(L.first_path % kTangentTile == 0);
+    const unsigned long long local0 = (unsigned long long)blockIdx.x * kTangentTile;
+    const unsigned long long g0 = L.first_path + local0;         // multiple of the tile: no carry below
+    uint32_t path_hi = (uint32_t)(g0 >> 32);
+    asm volatile("" : "+r"(path_hi));
+    const uint32_t path_lo0 = (uint32_t)g0 + threadIdx.x;
+    NMCHB_ASSERT(((g0 + (unsigned long long)(kTangentTile - 1)) >> 32) == (g0 >> 32));
+    const FePoint pc = L.pt0;
+
+    float S[P], V[P], A[P], B[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        S[j] = L.S0;
+        V[j] = L.v0;
+        A[j] = 1.0f;
+        B[j] = 0.0f;
+    }
+    const unsigned long long w0 = L.draw_offset;
+    unsigned long long blk = w0 >> 2;
+    int n = L.N;
+    const bool resume = (w0 & 2ull) != 0ull && n > 0;            // start on the second word pair of a block
+    if (resume) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * kTangentThreads, path_hi, L.keys);
+            fe_step_native_tangent<FLOOR>(S[j], V[j], A[j], B[j], w.z, w.w, L.rdt, L.zr, L.zc, pc);
         }
-        fe_step_native_tangent<FLOOR>(S, V, A, B, second ? w.z : w.x, second ? w.w : w.y, L.rdt, L.zr, L.zc, L.pt0);
+    }
+    blk += resume ? 1ull : 0ull;
+    n -= resume ? 1 : 0;
+    int pairs = n >> 1;
+    while (pairs > 0) {
+        const uint32_t blk_hi = (uint32_t)(blk >> 32);
+        const uint32_t blk_lo = (uint32_t)blk;
+        const unsigned long long room = 0x100000000ull - (unsigned long long)blk_lo;
+        const int chunk = ((unsigned long long)pairs < room) ? pairs : (int)room;
+        PhiloxPathInv inv[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) inv[j] = philox_path_invariants(blk_hi, path_lo0 + j * kTangentThreads, L.keys);
+#pragma unroll 1
+        for (int it = 0; it < chunk; ++it) {
+            const PhiloxBlockUniform bu = philox_block_uniform(blk_lo + (uint32_t)it, path_hi, L.keys);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const U4 w = philox4x32_10_hoisted(bu, inv[j], L.keys);
+                fe_step_native_tangent<FLOOR>(S[j], V[j], A[j], B[j], w.x, w.y, L.rdt, L.zr, L.zc, pc);
+                fe_step_native_tangent<FLOOR>(S[j], V[j], A[j], B[j], w.z, w.w, L.rdt, L.zr, L.zc, pc);
+            }
+        }
+        blk += (unsigned long long)chunk;
+        pairs -= chunk;
+    }
+    if (n & 1) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const U4 w = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), path_lo0 + j * kTangentThreads, path_hi, L.keys);
+            fe_step_native_tangent<FLOOR>(S[j], V[j], A[j], B[j], w.x, w.y, L.rdt, L.zr, L.zc, pc);
+        }
     }
     double pay = 0.0, pay2 = 0.0;
-    if (active) {
-        pay = payoff_or_nan(S, L.K);
-        pay2 = pay * pay;
-        S_out[idx] = S;
-        V_out[idx] = V;
-        B_out[idx] = B;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const unsigned long long idx = local0 + (unsigned long long)(j * kTangentThreads) + threadIdx.x;
+        if (idx < L.n_local) {
+            const double x = payoff_or_nan(S[j], L.K);
+            pay += x;
+            pay2 += x * x;
+            S_out[idx] = S[j];
+            V_out[idx] = V[j];
+            B_out[idx] = B[j];
+        }
     }
     block_reduce_and_finish(pay, pay2, rb.partials, rb.tickets, rb.out, 0, blockIdx.x, L.blocks_per_point);
 }
@@ -102,7 +157,7 @@ cudaError_t launch_fe_tangent(const FeLaunch &L, int floor_kind, ReduceBuffers r
         info->grid_x = (int)grid.x;
         info->grid_y = 1;
         info->block_threads = kTangentThreads;
-        info->paths_per_thread = 1;
+        info->paths_per_thread = kTangentPaths;
         cudaFuncAttributes fa{};
         const void *fn = floor_kind == kFloorAbs ? (const void *)fe_tangent_kernel<kFloorAbs> : (const void *)fe_tangent_kernel<kFloorPlus>;
         if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) info->regs_per_thread = fa.numRegs;
@@ -120,5 +175,6 @@ cudaError_t launch_strike_greeks(const float *d_S, const float *d_B, unsigned lo
 }
 
 int greek_blocks_per_slot() { return kGreekBlocks; }
+int tangent_tile_paths() { return kTangentTile; }
 
 }  // namespace nmchb

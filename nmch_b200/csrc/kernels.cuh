@@ -97,6 +97,7 @@ cudaError_t launch_fe_tangent(const FeLaunch &L, int floor_kind, ReduceBuffers r
 cudaError_t launch_strike_greeks(const float *d_S, const float *d_B, unsigned long long n_local, const float *d_strikes,
                                  int n_strikes, float S0, ReduceBuffers rb, cudaStream_t stream);
 int greek_blocks_per_slot();
+int tangent_tile_paths();                 // paths per block of fe_tangent_kernel
 
 // xorwow.cu
 struct XorwowSkipTables;                // device tables M_m^q, q = 1..3, m = 0..31
