@@ -20,7 +20,9 @@ BASELINE.json's metric has a second half and a second workload, carried as sub-r
   c5_strong  configs[4]: FE and EM at 2^30 GLOBAL paths sharded over the N ranks (strong scaling), 3 steps each
   c4_sweep   configs[3]: the 20^3 (kappa, theta, sigma) grid with the reference's skip filter (7778 points), 2^20 GLOBAL
              paths per point sharded over the N ranks, ONE launch per method + one allreduce of 2 x 7778 moments
-  other_floor (N=1)  configs[1] names both variance floors: the (.)+ floor on the headline workload
+  other_floor (N=1)  configs[1] names both variance floors: the (.)+ floor on the headline workload, with the reference's
+             CUDA build of that floor (its one floor token changed while compiling, oracle/_ref/nmch_ref_harness_plus)
+             timed beside it and compared on the same seed
   group_check (N>1)  the single-process group front end (nmch_group_*: ncclCommInitAll, what the C++ classes and
              `--gpus` use) over the same N devices, run by rank 0 after the timed regions: its sums against the
              torch.distributed path's and its time per step
@@ -150,8 +152,8 @@ def cpu_baseline(method: str, N: int, budget_s: float = 12.0):
                       f"paths and excluded from value, like the reference's Tim_init)"}
 
 
-def _harness(method, rng, n, N, calls, kernel="k3"):
-    exe = os.path.join(ROOT, "oracle", "_ref", "nmch_ref_harness")
+def _harness(method, rng, n, N, calls, kernel="k3", plus_floor=False):
+    exe = os.path.join(ROOT, "oracle", "_ref", "nmch_ref_harness_plus" if plus_floor else "nmch_ref_harness")
     r = subprocess.run([exe, "--method", method, "--rng", rng, "--kernel", kernel, "--NTPB", "512", "--NB", str(n // 512),
                         "--N", str(N), "--repeat", str(calls)], capture_output=True, text=True, timeout=900, check=True)
     return [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
@@ -248,6 +250,36 @@ def reference_cuda(method: str, log2_paths: int, N: int, repeat: int = 3, with_o
                         "(NMCH_RNG_XORWOW_FAST); ours_native_same_words (Philox tag) = the DEFAULT native mode, which "
                         "consumes the same Philox words and uniforms with fast transforms; max_rel_diff_* against run 1 of the reference and against the mean "
                         "of its runs, to be read against own_spread")
+    return out
+
+
+def reference_cuda_plus_floor(n: int, N: int, repeat: int = 3):
+    """configs[1], the (.)+ side: the reference's CUDA build with its floor token `Vt = abs(Vt);` compiled as
+    `Vt = fmaxf(Vt, 0.0f);` (oracle/Makefile: _ref/nmch_ref_harness_plus -- the reference codes only abs), and this
+    engine on the same seed and calls: the draw-compatible mode of the tag and the fast mode on the same draws."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "nmch_ref_harness_plus")):
+        return None
+    from nmch_b200 import engine as E
+    out = {"what": "reference NMCH_FE_K3_MM<rng> with the floor token changed to (.)+ while compiling (-O3 -arch=sm_100), "
+                   f"512 x {n // 512} paths, N={N}, best Tim_exec of {repeat} after one warm-up compute(); ours on the same "
+                   "seed and calls with floor = plus: max relative difference of E and of the variance"}
+    for rng, modes in (("xorwow", (("ours_same_draws", E.RNG_XORWOW_COMPAT), ("ours_same_stream_fast", E.RNG_XORWOW_FAST))),
+                       ("philox", (("ours_same_draws", E.RNG_PHILOX_COMPAT), ("ours_native_same_words", E.RNG_PHILOX)))):
+        try:
+            rows = _harness("fe", rng, n, N, repeat + 1, plus_floor=True)[1:]
+            ms = min(x["exec_ms"] for x in rows)
+            out[rng] = {"value": n * N / (ms * 1e-3), "exec_ms": ms, "E": rows[-1]["E"], "E2": rows[-1]["E2"]}
+            for tag, mode in modes:
+                with E.Engine(NTPB=512, NB=n // 512, N=N, rng=mode, floor=E.FLOOR_PLUS, **README) as eng:
+                    eng.init(1234)
+                    eng.compute()
+                    ours = [eng.compute() for _ in range(repeat)]
+                best = min(o_.exec_ms for o_ in ours)
+                out[rng][tag] = {"value": n * N / (best * 1e-3), "exec_ms": best,
+                                 "max_rel_diff_E": max(abs(o_.mean - r_["E"]) / abs(r_["E"]) for o_, r_ in zip(ours, rows)),
+                                 "max_rel_diff_var": max(abs(o_.variance - _var(r_)) / _var(r_) for o_, r_ in zip(ours, rows))}
+        except Exception as ex:  # noqa: BLE001
+            out[rng] = {"error": str(ex)[:200]}
     return out
 
 
@@ -594,6 +626,8 @@ def main():
                                        "E[X]": runs[-1].mean, "std_error": runs[-1].std_error,
                                        "note": "BASELINE configs[1] is FE with the |.| floor vs the (.)+ floor: the headline is "
                                                "the reference's floor (|.|, the only one it codes), this is the other"}
+                if other == E.FLOOR_PLUS and not args.no_reference_cuda:
+                    line["other_floor"]["reference_cuda"] = reference_cuda_plus_floor(n_per_gpu, N)
             except Exception as ex:  # noqa: BLE001
                 line["other_floor"] = {"error": str(ex)[:200]}
             try:                                  # the opt-in dense-draw stream, same workload, for the record

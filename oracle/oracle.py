@@ -17,6 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 CURAND_HOST_PATH = os.path.join(HERE, "_ref", "libcurand_host.so")
 REF_HARNESS_PATH = os.path.join(HERE, "_ref", "nmch_ref_harness")
+# the same build with the FE floor token changed to (.)+ (oracle/Makefile: _ref/nmch_ref_harness_plus)
+REF_HARNESS_PLUS_PATH = os.path.join(HERE, "_ref", "nmch_ref_harness_plus")
 
 RNG_XORWOW, RNG_PHILOX, RNG_MRG32K3A, RNG_PHILOX_DENSE = 0, 1, 2, 3
 FLOOR_ABS, FLOOR_PLUS = 0, 1

@@ -81,3 +81,18 @@ def test_sub_records_em_and_c5_strong():
     c4 = d["c4_sweep"]
     for m in ("fe", "em"):
         assert c4[m]["gpu_launches"] == 1 and c4[m]["all_finite"] and c4[m]["points"] == 200 and c4[m]["launch_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_other_floor_record_carries_the_reference_build_with_the_plus_floor():
+    """configs[1] names both floors; the (.)+ side of the reference is its CUDA build with the floor token changed while
+    compiling (oracle/_ref/nmch_ref_harness_plus).  Same seed, same calls: 1e-5 on price and variance."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "nmch_ref_harness_plus")):
+        pytest.skip("oracle/_ref/nmch_ref_harness_plus not shipped")
+    d = _run("--steps", "3", "--warmup", "3", "--log2-paths", "18", "--c5-log2-paths", "20", "--c4-log2-paths", "12", "--c4-points", "4",
+             "--no-cpu-baseline")
+    ref = d["other_floor"]["reference_cuda"]
+    for rng, tags in (("xorwow", ("ours_same_draws", "ours_same_stream_fast")), ("philox", ("ours_same_draws", "ours_native_same_words"))):
+        assert ref[rng]["exec_ms"] > 0
+        for tag in tags:
+            assert ref[rng][tag]["max_rel_diff_E"] < 1e-5 and ref[rng][tag]["max_rel_diff_var"] < 1e-5, (rng, tag, ref[rng][tag])

@@ -91,10 +91,10 @@ def test_compat_shard_offsets_select_subsequences():
 # ---------------------------------------------------------------------------------------------
 # compat modes vs the reference's CUDA build
 # ---------------------------------------------------------------------------------------------
-def _ref_cuda(**flags):
-    exe = o.REF_HARNESS_PATH
+def _ref_cuda(plus_floor=False, **flags):
+    exe = o.REF_HARNESS_PLUS_PATH if plus_floor else o.REF_HARNESS_PATH
     if not os.path.exists(exe):
-        pytest.skip("oracle/_ref/nmch_ref_harness not shipped")
+        pytest.skip("oracle/_ref/nmch_ref_harness[_plus] not shipped")
     cmd = [exe]
     for k, v in flags.items():
         cmd += [f"--{k}", str(v)]
@@ -123,6 +123,25 @@ def test_compat_matches_reference_cuda_build(rng_name, rng_e, cfg):
             # float-atomic accumulation carries ~1e-6 of noise at this size)
             assert _rel(m.mean, r["E"]) < 1e-5, (call, m.mean, r["E"])
             assert _rel(m.variance, var_ref) < 1e-5, (call, m.variance, var_ref)
+
+
+@pytest.mark.parametrize("rng_name,modes", [("xorwow", (1, 5)), ("philox", (2, 0)), ("mrg", (3,))])
+@pytest.mark.parametrize("cfg", [dict(NTPB=512, NB=512, N=1000), dict(NTPB=512, NB=512, N=1000, k=2.08, theta=0.108, sigma=1.0)])
+def test_plus_floor_matches_the_reference_cuda_build_with_its_floor_token_changed(rng_name, modes, cfg):
+    """BASELINE configs[1] ("|.| floor vs (.)+ floor ... vs reference CUDA build"): the reference codes only abs, so the
+    other side is its build with `Vt = abs(Vt);` compiled as `Vt = fmaxf(Vt, 0.0f);` (oracle/Makefile).  Both the
+    draw-compatible mode of the tag and the fast mode on the same draws (XORWOW_FAST / native Philox) hold 1e-5."""
+    ref = _ref_cuda(plus_floor=True, method="fe", rng=rng_name, kernel="k3", repeat=2, **cfg)
+    kw = {k: cfg[k] for k in ("k", "theta", "sigma") if k in cfg}
+    for mode in modes:
+        with E.Engine(NTPB=cfg["NTPB"], NB=cfg["NB"], N=cfg["N"], rng=mode, floor=E.FLOOR_PLUS, **kw) as e:
+            e.init(1234)
+            for call in range(2):
+                m = e.compute()
+                r = ref[call]
+                assert r["cuda"] == "cudaSuccess"
+                assert _rel(m.mean, r["E"]) < 1e-5, (mode, call, m.mean, r["E"])
+                assert _rel(m.variance, r["E2"] - r["E"] ** 2) < 1e-5, (mode, call, m.variance, r["E2"] - r["E"] ** 2)
 
 
 # ---------------------------------------------------------------------------------------------

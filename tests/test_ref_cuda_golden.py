@@ -110,3 +110,63 @@ def test_engine_compat_sweep_reproduces_reference_cuda(sw):
         got = e.explore(k, th, sg)                      # one launch == the reference's sequential set_* + compute()
     for m, want in zip(got, sw["calls"]):
         assert _rel(m.mean, want["E"]) < 2e-5, (m.mean, want["E"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The (.)+ floor -- BASELINE configs[0] / configs[1].  The reference documents it (README.md:37-40) but codes only abs
+# (NMCH_FE.cu:47,162,218,222,281), so the reference side of this comparison is its CUDA build with that ONE token
+# changed while compiling (oracle/Makefile: _ref/nmch_ref_harness_plus; fixtures: make_ref_cuda_golden.py --plus).
+# ---------------------------------------------------------------------------------------------------------------------
+GOLD_PLUS = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cuda_b200_plus.json")))
+_ID = lambda c: "{rng}-{NTPB}x{NB}-N{N}".format(**c["flags"])  # noqa: E731
+
+
+def test_plus_floor_fixtures_differ_from_the_abs_floor_where_feller_fails():
+    a = next(c for c in GOLD["cases"] if c["flags"].get("k") == 2.08 and c["flags"]["rng"] == "xorwow" and c["flags"]["NB"] == 512)
+    p = next(c for c in GOLD_PLUS["cases"] if c["flags"].get("k") == 2.08 and c["flags"]["rng"] == "xorwow" and c["flags"]["NB"] == 512)
+    assert a["flags"] == p["flags"]
+    assert abs(a["calls"][0]["E"] - p["calls"][0]["E"]) > 5e-4          # 0.112979 vs 0.111988
+    assert abs(p["calls"][0]["E"] - 0.111988764) < 2e-6                  # the survey's host value for this case
+
+
+@pytest.mark.parametrize("case", GOLD_PLUS["cases"], ids=_ID)
+def test_oracle_fe_plus_floor_reproduces_patched_reference_cuda(case):
+    f = case["flags"]
+    n = f["NTPB"] * f["NB"]
+    rng = {"xorwow": o.RNG_XORWOW, "philox": o.RNG_PHILOX, "mrg": o.RNG_MRG32K3A}[f["rng"]]
+    for call, want in enumerate(case["calls"], start=1):
+        got = o.fe_run(_params(f), rng=rng, floor=o.FLOOR_PLUS, n_paths=n, calls=call)
+        assert _rel(got["mean"], want["E"]) < 1e-5, (call, got["mean"], want["E"])
+        var_ref = want["E2"] - want["E"] ** 2
+        assert _rel(got["mean_sq"] - got["mean"] ** 2, var_ref) < 1e-5 + 4 * want["E2_spread"] / var_ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD_PLUS["cases"], ids=_ID)
+def test_engine_compat_plus_floor_reproduces_patched_reference_cuda(case):
+    from nmch_b200 import engine as E
+    f = case["flags"]
+    kw = {k: f[k] for k in PKEYS if k in f}
+    modes = {"xorwow": [E.RNG_XORWOW_COMPAT, E.RNG_XORWOW_FAST], "philox": [E.RNG_PHILOX_COMPAT, E.RNG_PHILOX],
+             "mrg": [E.RNG_MRG32K3A_COMPAT]}[f["rng"]]
+    for mode in modes:          # the draw-compatible checker AND the fast mode on the same draws (native / XORWOW_FAST)
+        with E.Engine(NTPB=f["NTPB"], NB=f["NB"], N=f["N"], rng=mode, floor=E.FLOOR_PLUS, **kw) as e:
+            e.init(1234)
+            for want in case["calls"]:
+                m = e.compute()
+                var_ref = want["E2"] - want["E"] ** 2
+                assert _rel(m.mean, want["E"]) < 1e-5 + 4 * want["E_spread"] / want["E"], (mode, m.mean, want)
+                assert _rel(m.variance, var_ref) < 1e-5 + 4 * want["E2_spread"] / var_ref, (mode, m.variance, var_ref)
+
+
+@pytest.mark.gpu
+def test_engine_compat_plus_floor_sweep_reproduces_patched_reference_cuda():
+    from nmch_b200 import engine as E
+    sw = GOLD_PLUS["sweeps"][0]
+    f = sw["flags"]
+    k, th, sg = (np.array(x, np.float32) for x in zip(*sw["points"]))
+    with E.Engine(NTPB=f["NTPB"], NB=f["NB"], N=f["N"], rng=E.RNG_XORWOW_COMPAT, floor=E.FLOOR_PLUS) as e:
+        e.init(1234)
+        got = e.explore(k, th, sg)
+    for m, want in zip(got, sw["calls"]):
+        assert _rel(m.mean, want["E"]) < 2e-5, (m.mean, want["E"])
