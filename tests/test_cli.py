@@ -140,3 +140,82 @@ def test_exploration_bias_column_and_linspace_grid():
     assert pd.to_numeric(df["bias"], errors="coerce").notna().all()
     worst = max(rows, key=lambda x: abs(float(x[6])))
     assert abs(float(worst[6])) < 0.03, worst                  # Euler bias (sigma = 1 corners) + MC noise stay small
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Text-level drop-in check against the reference's OWN command line tools: oracle/_ref/nmch_ref_cli and
+# oracle/_ref/nmch_ref_exploration are src/NMCH/test/nmch.cu and exploration.cu compiled unmodified (oracle/Makefile).
+# Same command line in, same text out -- up to the last printed digit of the estimates (float atomics on their side) and
+# the two timing lines.
+# ---------------------------------------------------------------------------------------------------------------------
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "nmch_ref_cli")
+REF_EXPL = os.path.join(ROOT, "oracle", "_ref", "nmch_ref_exploration")
+
+
+def _same_text_close_number(ours, ref, abs_tol, rel_tol):
+    a, b = ours.rsplit(" ", 1), ref.rsplit(" ", 1)
+    assert a[0] == b[0], (ours, ref)
+    x, y = float(a[1]), float(b[1])
+    assert abs(x - y) <= abs_tol + rel_tol * abs(y), (ours, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,extra", [
+    (("--method", "fe", "--NB", 64, "--N", 200), ()),                          # Philox tag -> our default fast mode
+    (("--method", "fe", "--NB", 64, "--N", 200), ("--rng", "philox-compat")),  # ... and the draw-compatible checker
+    (("--method", "fe", "--NTPB", 256, "--NB", 128, "--N", 365, "--T", 0.5, "--S_0", 2.0, "--v_0", 0.04, "--r", 0.03, "--k", 1.5,
+      "--rho", 0.3, "--theta", 0.09, "--sigma", 0.5, "--seed", 77), ()),
+    (("--method", "em", "--NB", 64, "--N", 200), ("--rng", "philox-compat")),  # the reference's EM draws (its bias included)
+])
+def test_nmch_prints_what_the_reference_cli_prints(args, extra):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/nmch_ref_cli not shipped")
+    ref = run(REF_CLI, *args)
+    ours = run(NMCH, *args, *extra)
+    assert ref.returncode == 0 and ours.returncode == 0, (ref.stderr, ours.stderr)
+    r, o_ = ref.stdout.splitlines(), ours.stdout.splitlines()
+    assert len(r) == len(o_) == 19
+    assert o_[:13] == r[:13]                                   # parameter block and METHOD line, byte for byte
+    _same_text_close_number(o_[13], r[13], 2e-6, 1e-5)         # E[X]
+    _same_text_close_number(o_[14], r[14], 2e-6, 1e-5)         # E[X^2]
+    assert o_[15] == r[15]                                     # "The true price ..." (their Black-Scholes line)
+    _same_text_close_number(o_[16], r[16], 2e-6, 1e-4)         # 95 % error
+    for i in (17, 18):                                         # timings: same words, own numbers
+        assert o_[i].rsplit(" ", 2)[0] == r[i].rsplit(" ", 2)[0] and o_[i].endswith(" ms")
+
+
+@pytest.mark.gpu
+def test_nmch_help_and_errors_read_like_the_reference():
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/nmch_ref_cli not shipped")
+    r, o_ = run(REF_CLI, "--help"), run(NMCH, "--help")
+    assert r.returncode == o_.returncode == 0
+    rl, ol = r.stdout.splitlines(), o_.stdout.splitlines()
+    assert ol[1:len(rl)] == rl[1:]                             # every reference line, in order (ours adds flags after them)
+    assert rl[0].startswith("Usage: ") and ol[0].startswith("Usage: ")
+    r, o_ = run(REF_CLI, "--method", "heun"), run(NMCH, "--method", "heun")
+    assert (r.returncode, r.stdout) == (o_.returncode, o_.stdout)
+
+
+@pytest.mark.gpu
+def test_exploration_prints_what_the_reference_exploration_prints():
+    """The reference's tool takes no arguments (512 x 10 paths, N = 1000, seed 1234, XORWOW tag, 200 FE + 200 EM points on
+    continued streams).  Ours, run without arguments, must print the same CSV: same header, same rows in the same order with
+    byte-identical method / k / theta / sigma fields, the err column equal to the printed precision (FE: all 200 rows; EM:
+    the draw-compatible stream reproduces the reference's accept/reject decisions, so its rows match too)."""
+    if not os.path.exists(REF_EXPL):
+        pytest.skip("oracle/_ref/nmch_ref_exploration not shipped")
+    ref, ours = run(REF_EXPL), run(EXPL)
+    assert ref.returncode == 0 and ours.returncode == 0, (ref.stderr, ours.stderr)
+    r, o_ = ref.stdout.splitlines(), ours.stdout.splitlines()
+    assert o_[0] == r[0] and len(o_) == len(r) == 401
+    worst = {"fe": 0.0, "em": 0.0}
+    for a, b in zip(o_[1:], r[1:]):
+        fa, fb = a.split(", "), b.split(", ")
+        assert fa[:4] == fb[:4], (a, b)
+        assert len(fa) == len(fb) == 6
+        d = abs(float(fa[5]) - float(fb[5])) / float(fb[5])
+        worst[fa[0]] = max(worst[fa[0]], d)
+    # err ~ 5e-3 printed with 6 decimals: one unit of the last digit is 2e-4 relative
+    assert worst["fe"] < 4e-4, worst
+    assert worst["em"] < 4e-4, worst
