@@ -8,7 +8,7 @@
  * Everything numerical below is the reference's code: this file only parses flags, calls
  * init/compute through the public API and prints what the getters return.
  *
- *   nmch_ref_harness --method fe|em --rng xorwow|philox|mrg [--kernel k1|k2|k3] --NTPB .. --NB .. --N ..
+ *   nmch_ref_harness --method fe|em --rng xorwow|philox|mrg [--kernel k1|k2|k3|k2philox|k1pgm|k1pim] --NTPB .. --NB .. --N ..
  *                    (k1 = NMCH_*_K1_MM: needs a power-of-two NTPB, stores E[X^2]/n^2 in price_squared)
  *                    [--k --theta --sigma --rho --T --S_0 --v_0 --r --seed] [--repeat R]
  *                    [--points FILE]   (lines "k theta sigma": one set_* + compute() per line)
@@ -112,6 +112,9 @@ int main(int argc, char **argv)
         if (a.kernel == "k2") return x ? run<NMCH_FE_K2_MM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K2_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k3") return x ? run<NMCH_FE_K3_MM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K3_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k2philox") return run<NMCH_FE_K2_PHILOX_MM>(a);
+        // the pageable / pinned host-memory variants of the K1 class (NMCH_FE.hpp:168,180)
+        if (a.kernel == "k1pgm") return x ? run<NMCH_FE_K1_PgM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K1_PgM<curandStatePhilox4_32_10_t>>(a);
+        if (a.kernel == "k1pim") return x ? run<NMCH_FE_K1_PiM<curandStateXORWOW_t>>(a) : run<NMCH_FE_K1_PiM<curandStatePhilox4_32_10_t>>(a);
     } else if (a.method == "em") {
         if (a.kernel == "k1") return x ? run<NMCH_EM_K1_MM<curandStateXORWOW_t>>(a) : run<NMCH_EM_K1_MM<curandStatePhilox4_32_10_t>>(a);
         if (a.kernel == "k2") return x ? run<NMCH_EM_K2_MM<curandStateXORWOW_t>>(a) : run<NMCH_EM_K2_MM<curandStatePhilox4_32_10_t>>(a);
