@@ -125,6 +125,24 @@ def test_compat_matches_reference_cuda_build(rng_name, rng_e, cfg):
             assert _rel(m.variance, var_ref) < 1e-5, (call, m.variance, var_ref)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 0xFEDCBA9876543210, (1 << 63) + 12345])
+@pytest.mark.parametrize("rng_name,modes", [("xorwow", (1, 5)), ("philox", (2, 0)), ("mrg", (3,))])
+def test_other_seeds_match_the_reference_cuda_build(seed, rng_name, modes):
+    """Seeds beyond 1234: zero, one, and 64-bit seeds whose high half is non-zero (XORWOW scrambles both halves,
+    curand_kernel.h:807-818; Philox takes them as its two key words; MRG32k3a derives six state words from them)."""
+    cfg = dict(NTPB=256, NB=256, N=200)
+    ref = _ref_cuda(method="fe", rng=rng_name, kernel="k3", repeat=2, seed=seed, **cfg)
+    for mode in modes:
+        with E.Engine(rng=mode, **cfg) as e:
+            e.init(seed)
+            for call in range(2):
+                m = e.compute()
+                r = ref[call]
+                assert r["cuda"] == "cudaSuccess"
+                assert _rel(m.mean, r["E"]) < 1e-5, (mode, seed, call, m.mean, r["E"])
+                assert _rel(m.variance, r["E2"] - r["E"] ** 2) < 1e-5, (mode, seed, call)
+
+
 @pytest.mark.parametrize("rng_name,modes", [("xorwow", (1, 5)), ("philox", (2, 0)), ("mrg", (3,))])
 @pytest.mark.parametrize("cfg", [dict(NTPB=512, NB=512, N=1000), dict(NTPB=512, NB=512, N=1000, k=2.08, theta=0.108, sigma=1.0)])
 def test_plus_floor_matches_the_reference_cuda_build_with_its_floor_token_changed(rng_name, modes, cfg):
