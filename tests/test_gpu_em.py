@@ -87,6 +87,26 @@ def test_compat_matches_reference_cuda_build(rng_name, rng_e, cfg):
             assert _rel(m.variance, r["E2"] - r["E"] ** 2) < 1e-5, (call, m.variance)
 
 
+@pytest.mark.parametrize("seed", [0, 0xFEDCBA9876543210])
+@pytest.mark.parametrize("rng_name,rng_e", [("xorwow", 1), ("philox", 2), ("mrg", 3)])
+@pytest.mark.parametrize("cfg", [dict(NTPB=256, NB=64, N=200), dict(NTPB=256, NB=64, N=200, k=10.0, theta=0.5, sigma=1.0),
+                                 dict(NTPB=256, NB=64, N=120, T=0.5, v_0=0.04, k=1.5, rho=0.3, theta=0.09, sigma=0.5)])
+def test_compat_other_seeds_and_parameters_match_the_reference_cuda_build(seed, rng_name, rng_e, cfg):
+    """Other seeds (zero; 64 bits with a non-zero high half) and parameter sets (large shape and noncentrality; T != 1 with the
+    reference's own T = 1 formula for the terminal draw, NMCH_EM.cu:116): the draw-compatible mode follows every accept /
+    reject decision of the reference's cuRAND samplers."""
+    ref = _ref_cuda(method="em", rng=rng_name, kernel="k3", repeat=2, seed=seed, **cfg)
+    kw = {k: cfg[k] for k in ("T", "v_0", "k", "rho", "theta", "sigma") if k in cfg}
+    with E.Engine(NTPB=cfg["NTPB"], NB=cfg["NB"], N=cfg["N"], method=E.METHOD_EM, rng=rng_e, **kw) as e:
+        e.init(seed)
+        for call in range(2):
+            m = e.compute()
+            r = ref[call]
+            assert r["cuda"] == "cudaSuccess"
+            assert _rel(m.mean, r["E"]) < 1e-5, (call, m.mean, r["E"])
+            assert _rel(m.variance, r["E2"] - r["E"] ** 2) < 1e-5, (call, m.variance)
+
+
 def test_compat_reproduces_reference_bias():
     # SURVEY.md §7-4: the reference EM is biased low (E = 0.11718 at 2^18 paths, -7.5 SE vs analytic)
     n = 1 << 18
